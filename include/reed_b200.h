@@ -1,0 +1,122 @@
+/* C-ABI of libreed_sm100.so - the B200 (sm_100a) drop-in for the REED image hot path.
+ *
+ * The reference (ChenyuWang-Monica/REED) has no native code on this path: its SiT training step is Python over
+ * PyTorch library kernels.  Each entry point below therefore replaces the PyTorch call sequence at the cited
+ * reference lines (paths relative to /root/reference/image); the Python-side binding is reed_b200/_cabi.py
+ * (ctypes), wrapped as autograd functions in reed_b200/ops.py.  INTEGRATION.md shows the stub a maintainer adds.
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on error; reed_last_error() returns the thread-local message
+ *   - plain pointers and sizes only; all buffers are device memory owned by the caller (PyTorch's allocator);
+ *     the library allocates nothing persistent and never synchronises: calls only enqueue work on `stream`
+ *   - `stream` is a cudaStream_t passed as void*; re-entrant, no global "current stream"
+ *   - dtype codes: 0 = float32, 1 = bfloat16.  "act dtype" is the activation dtype of the precision mode
+ *     (0: fp32 mode, parity bar 1e-5 relative; 1: bf16 tensor-core mode, parity bar 2e-2 relative)
+ *   - backend codes (gemm/attention): 0 = auto, 1 = force the fp32-math SIMT kernel, 2 = require the tensor-core kernel
+ */
+#ifndef REED_B200_H_
+#define REED_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+int reed_version(void);
+const char* reed_last_error(void);
+/* 0 iff the current CUDA device is an sm_100 part; copies its name into `name` when non-NULL. */
+int reed_device_check(char* name, int name_len);
+
+/* D[M,N] = epilogue(A[M,K] . B[N,K]^T)   -- every nn.Linear of the model and its dgrad/wgrad.
+ * Replaces: timm Attention.qkv/.proj and Mlp.fc1/.fc2 (models/sit.py:114-124,134-135), adaLN linears (125-133,
+ * 148-154), projector MLP (17-24, 292-301), t-embedder MLP (38-42, 69), patch-embed conv as a linear (198-200, 279),
+ * final linear (147, 156), and autograd's dgrad/wgrad GEMMs for all of them.
+ *   a_mn_major / b_mn_major: 0 = operand stored [rows, K] (K contiguous); 1 = stored [K, rows] (rows contiguous).
+ *     forward y = x W^T : (0, 0);  dgrad dx = dy W : A = dy (0), B = W stored [N_out, K_in] (1);
+ *     wgrad dW = dy^T x : A = dy stored [M, N_out] (1), B = x stored [M, K_in] (1).
+ *   epilogue: 0 none (+bias; `accumulate` adds into fp32 D)          1 GELU(tanh)   2 SiLU  (pre-activation -> out2)
+ *             3 D = aux + gate[row / rows_per_group] * (acc + bias)   (aux fp32 residual; y -> out2)
+ *             4 D = acc * gelu_tanh'(aux)   5 D = acc * silu'(aux)     (aux = saved pre-activation, act dtype)
+ *   bias: fp32 [N] or NULL.  gate: fp32 rows of pitch ld_gate.  out2: act dtype, pitch ld_out2, or NULL. */
+int reed_gemm(int act_dtype, const void* A, int64_t lda, int a_mn_major, const void* B, int64_t ldb, int b_mn_major,
+              void* D, int64_t ldd, int d_dtype, int M, int N, int K, int epilogue, const void* bias, const void* aux,
+              int64_t ld_aux, const void* gate, int64_t ld_gate, int rows_per_group, void* out2, int64_t ld_out2,
+              int accumulate, int backend, void* stream);
+
+/* Multi-head attention, non-causal, scale head_dim^-0.5, over the packed qkv GEMM output.
+ * Replaces timm Attention.forward's reshape/permute + F.scaled_dot_product_attention (models/sit.py:13,114-118,134).
+ *   qkv [B,T,3,H,hd] (act dtype) -> o [B,T,H,hd] (act dtype), lse [B,H,T] fp32 (saved for backward). */
+int reed_attn_fwd(int act_dtype, const void* qkv, void* o, void* lse, int B, int T, int H, int hd, int backend,
+                  void* stream);
+/* dqkv [B,T,3,H,hd] from d_o [B,T,H,hd]; delta [B,H,T] fp32 is workspace (rowsum(dO*O)). */
+int reed_attn_bwd(int act_dtype, const void* qkv, const void* o, const void* d_o, const void* lse, void* dqkv,
+                  void* delta, int B, int T, int H, int hd, int backend, void* stream);
+
+/* out = LayerNorm(x; no affine, eps) * (1 + scale[g]) + shift[g], g = row / rows_per_group.
+ * Replaces norm1/norm2/norm_final + modulate (models/sit.py:26-27,113,119,134-135,146,155).
+ *   x fp32 [M,D]; shift/scale fp32 rows of pitch ld_mod; out act dtype [M,D]; mean/rstd fp32 [M] (saved). */
+int reed_ln_modulate_fwd(const void* x, const void* shift, const void* scale, int64_t ld_mod, int rows_per_group,
+                         void* out, int act_dtype, void* mean, void* rstd, int M, int D, float eps, void* stream);
+/* dx = dres + LN-backward(dout * (1+scale)); dshift[g] += sum dout; dscale[g] += sum dout * xhat (fp32 atomics).
+ * dres may be NULL.  Replaces autograd of the above plus the residual-gradient add. */
+int reed_ln_modulate_bwd(const void* dout, int act_dtype, const void* x, const void* mean, const void* rstd,
+                         const void* scale, int64_t ld_mod, int rows_per_group, const void* dres, void* dx,
+                         void* dshift, void* dscale, int M, int D, void* stream);
+/* Backward of x_new = x + gate[g] * y (models/sit.py:134-135): dy = gate * dxn (act dtype), dgate[g] += sum dxn * y,
+ * dbias (optional, fp32 [D]) += column sums of dy. */
+int reed_gate_bwd(const void* dxn, const void* y, int act_dtype, const void* gate, int64_t ld_mod, int rows_per_group,
+                  void* dy, void* dgate, void* dbias, int M, int D, void* stream);
+/* out[n] += sum_m src[m,n]  (bias gradients). */
+int reed_colsum(const void* src, int act_dtype, int64_t ld, void* out, int M, int N, void* stream);
+/* op 0: dtype cast; op 1: SiLU then cast (the SiLU in front of every adaLN linear, models/sit.py:126,149). */
+int reed_unary(const void* in, int in_dtype, void* out, int out_dtype, int op, int64_t n, void* stream);
+/* dx = dy * act'(h); act 1 = GELU(tanh), 2 = SiLU. */
+int reed_act_bwd(const void* dy, int d_dtype, const void* h, int h_dtype, void* dx, int act, int64_t n, void* stream);
+/* Token mean for the text projector (models/sit.py:292,301) and its backward. */
+int reed_group_mean_fwd(const void* x, void* out, int out_dtype, int groups, int rows_per_group, int D, void* stream);
+int reed_group_mean_bwd(const void* dy, void* dx, int groups, int rows_per_group, int D, int accumulate, void* stream);
+int reed_add_f32(const void* a, const void* b, void* out, int64_t n, void* stream);
+
+/* SILoss (loss.py).  path_type: 0 linear, 1 cosine.  t fp32 [batch].
+ * interp : x_t = alpha_t x + sigma_t eps                                    (loss.py:49-64,175-176)
+ * mse_fwd: denoise[b] = mean((pred - (dalpha x + dsigma eps))^2)             (loss.py:178-186)
+ * mse_bwd: dpred = g[b] * 2 (pred - target) / per_sample
+ * cos_fwd: align[b] += -(1/T) sum_t cos(z~[b,t], z[b,t]) (F.normalize eps 1e-12); stats [batch*T,3] saved (204-221)
+ * cos_bwd: dz~ from g[b]. */
+int reed_siloss_interp(const void* x, const void* eps, const void* t, void* xt, int batch, int per_sample,
+                       int path_type, void* stream);
+int reed_siloss_mse_fwd(const void* pred, const void* x, const void* eps, const void* t, void* denoise, int batch,
+                        int per_sample, int path_type, void* stream);
+int reed_siloss_mse_bwd(const void* pred, const void* x, const void* eps, const void* t, const void* g, void* dpred,
+                        int batch, int per_sample, int path_type, void* stream);
+int reed_siloss_cos_fwd(const void* zt, int zt_dtype, const void* z, int z_dtype, void* stats, void* align, int batch,
+                        int T, int Z, void* stream);
+int reed_siloss_cos_bwd(const void* zt, int zt_dtype, const void* z, int z_dtype, const void* stats, const void* g,
+                        void* dzt, int batch, int T, int Z, void* stream);
+
+/* One fused sampler update on the fp64 state (samplers.py:61-104 Euler/Heun, 124-187 Euler-Maruyama).
+ *   v: model output in model_dtype, n elements, or 2n (conditional half first) when guided.
+ *   sde=1: slope = v - 0.5*(2 t)*score(v, x, t) (samplers.py:15-43,150-151), else slope = v.
+ *   guided: slope = s_uncond + cfg * (s_cond - s_uncond).   d_prev != NULL: Heun corrector x + dt*(d_prev+slope)/2.
+ *   eps != NULL: + sqrt(2 t) * sqrt(|dt|) * eps.   d_out (optional) receives the guided slope.
+ *   x_model (optional) receives x_next cast to model_dtype, written twice when dup_out (next evaluation guided). */
+int reed_sampler_step(const void* x_cur, const void* v, int model_dtype, const void* eps, const void* d_prev,
+                      void* d_out, void* x_next, void* x_model, int64_t n, int guided, int dup_out, int sde,
+                      int path_type, double cfg, double t_cur, double dt, void* stream);
+int reed_sampler_cast(const void* x, void* x_model, int model_dtype, int64_t n, int dup, void* stream);
+
+/* Optimizer tail over flat fp32 buffers (train.py:94-105 update_ema, 253-259 AdamW, 402-412 clip/step/EMA).
+ * grad_sumsq: *out (double) += sum g^2.   adamw_ema: g *= grad_scale * min(1, max_norm/(grad_scale*sqrt(*norm_sq)+1e-6))
+ * (norm_sq NULL = no clipping), torch.optim.AdamW update with 1-based `step`, ema = decay*ema + (1-decay)*p, and
+ * (optional) bf16 shadow of the new weights for the GEMMs.  ema_update: EMA only (frozen pos_embed). */
+int reed_grad_sumsq(const void* g, int64_t n, void* out, void* stream);
+int reed_adamw_ema(void* p, const void* g, void* m, void* v, void* ema, void* shadow_bf16, int64_t n,
+                   const void* norm_sq, float max_norm, float grad_scale, float lr, float beta1, float beta2, float eps,
+                   float weight_decay, int step, float ema_decay, void* stream);
+int reed_ema_update(const void* p, void* ema, int64_t n, float decay, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* REED_B200_H_ */

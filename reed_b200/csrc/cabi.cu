@@ -1,0 +1,93 @@
+// C-ABI surface of libreed_sm100.so (declared in include/reed_b200.h).  Plain pointers and sizes only; every
+// call enqueues on the caller's stream and returns 0, or non-zero with a message in reed_last_error().
+#include <stdarg.h>
+#include "common.cuh"
+
+namespace reed {
+
+thread_local char g_err[512] = {0};
+
+int fail(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return 1;
+}
+
+int gemm_simt(int act_dtype, const void* A, int64_t lda, int a_mn, const void* B, int64_t ldb, int b_mn, void* D,
+              int64_t ldd, int d_dtype, int M, int N, int K, const EpiParams& ep, cudaStream_t st);
+int gemm_tcgen05(const void* A, int64_t lda, int a_mn, const void* B, int64_t ldb, int b_mn, void* D, int64_t ldd,
+                 int d_dtype, int M, int N, int K, const EpiParams& ep, cudaStream_t st);
+bool gemm_tcgen05_supported(int64_t lda, int64_t ldb, int64_t ldd, const void* A, const void* B, int M, int N, int K);
+int attn_simt_fwd(int act_dtype, const void* qkv, void* o, float* lse, int B, int T, int H, int hd, cudaStream_t st);
+int attn_simt_bwd(int act_dtype, const void* qkv, const void* o, const void* d_o, const float* lse, void* dqkv,
+                  float* delta, int B, int T, int H, int hd, cudaStream_t st);
+int attn_mma_fwd(const void* qkv, void* o, float* lse, int B, int T, int H, int hd, cudaStream_t st);
+int attn_mma_bwd(const void* qkv, const void* o, const void* d_o, const float* lse, void* dqkv, float* delta, int B,
+                 int T, int H, int hd, cudaStream_t st);
+bool attn_mma_supported(int T, int hd);
+
+}  // namespace reed
+
+using namespace reed;
+
+extern "C" int reed_version(void) { return 100; }   // 0.1.0
+
+extern "C" const char* reed_last_error(void) { return g_err; }
+
+// 0 when the current device is an sm_100 part; fills name (optional) with the device name
+extern "C" int reed_device_check(char* name, int name_len) {
+  int dev = 0;
+  REED_CHECK_CUDA(cudaGetDevice(&dev));
+  cudaDeviceProp prop;
+  REED_CHECK_CUDA(cudaGetDeviceProperties(&prop, dev));
+  if (name && name_len > 0) snprintf(name, name_len, "%s", prop.name);
+  REED_REQUIRE(prop.major == 10, "libreed_sm100 needs an sm_100 device, found sm_%d%d (%s)", prop.major, prop.minor, prop.name);
+  return 0;
+}
+
+// backend: 0 auto (tcgen05 for bf16 activations when the shape allows, else SIMT), 1 force SIMT, 2 require tcgen05
+extern "C" int reed_gemm(int act_dtype, const void* A, int64_t lda, int a_mn_major, const void* B, int64_t ldb,
+                         int b_mn_major, void* D, int64_t ldd, int d_dtype, int M, int N, int K, int epilogue,
+                         const void* bias, const void* aux, int64_t ld_aux, const void* gate, int64_t ld_gate,
+                         int rows_per_group, void* out2, int64_t ld_out2, int accumulate, int backend, void* stream) {
+  REED_REQUIRE(M >= 0 && N >= 0 && K >= 0, "gemm: negative dimension");
+  if (M == 0 || N == 0) return 0;
+  REED_REQUIRE(epilogue >= kEpiNone && epilogue <= kEpiDSilu, "gemm: unknown epilogue %d", epilogue);
+  REED_REQUIRE(!(accumulate && (epilogue != kEpiNone || d_dtype != kF32)), "gemm: accumulate needs fp32 D and no epilogue");
+  REED_REQUIRE(!(epilogue == kEpiGateRes && (d_dtype != kF32 || !aux || !gate || rows_per_group <= 0)),
+               "gemm: gate+residual epilogue needs fp32 D, residual, gate and rows_per_group");
+  REED_REQUIRE(!((epilogue == kEpiDGelu || epilogue == kEpiDSilu) && !aux), "gemm: act' epilogue needs the saved pre-activation");
+  EpiParams ep;
+  ep.kind = epilogue; ep.bias = (const float*)bias; ep.aux = aux; ep.ld_aux = ld_aux; ep.gate = (const float*)gate;
+  ep.ld_gate = ld_gate; ep.rows_per_group = rows_per_group > 0 ? rows_per_group : 1; ep.out2 = out2; ep.ld_out2 = ld_out2;
+  ep.accumulate = accumulate;
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool tc_ok = act_dtype == kBF16 && gemm_tcgen05_supported(lda, ldb, ldd, A, B, M, N, K) &&
+                     (ld_aux % 4 == 0) && (ld_out2 % 4 == 0) && (ld_gate % 4 == 0);
+  if (backend == 2) REED_REQUIRE(tc_ok, "gemm: tcgen05 path required but shape/dtype unsupported (M=%d N=%d K=%d)", M, N, K);
+  if (backend != 1 && tc_ok)
+    return gemm_tcgen05(A, lda, a_mn_major, B, ldb, b_mn_major, D, ldd, d_dtype, M, N, K, ep, st);
+  return gemm_simt(act_dtype, A, lda, a_mn_major, B, ldb, b_mn_major, D, ldd, d_dtype, M, N, K, ep, st);
+}
+
+// qkv: [B, T, 3, H, hd] (act dtype); o: [B, T, H, hd]; lse: [B, H, T] fp32
+extern "C" int reed_attn_fwd(int act_dtype, const void* qkv, void* o, void* lse, int B, int T, int H, int hd,
+                             int backend, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool mma_ok = act_dtype == kBF16 && attn_mma_supported(T, hd);
+  if (backend == 2) REED_REQUIRE(mma_ok, "attention: tensor-core path required but T=%d hd=%d unsupported", T, hd);
+  if (backend != 1 && mma_ok) return attn_mma_fwd(qkv, o, (float*)lse, B, T, H, hd, st);
+  return attn_simt_fwd(act_dtype, qkv, o, (float*)lse, B, T, H, hd, st);
+}
+
+// delta: [B, H, T] fp32 workspace (dO . O); dqkv: [B, T, 3, H, hd]
+extern "C" int reed_attn_bwd(int act_dtype, const void* qkv, const void* o, const void* d_o, const void* lse,
+                             void* dqkv, void* delta, int B, int T, int H, int hd, int backend, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool mma_ok = act_dtype == kBF16 && attn_mma_supported(T, hd);
+  if (backend == 2) REED_REQUIRE(mma_ok, "attention: tensor-core path required but T=%d hd=%d unsupported", T, hd);
+  if (backend != 1 && mma_ok) return attn_mma_bwd(qkv, o, d_o, (const float*)lse, dqkv, (float*)delta, B, T, H, hd, st);
+  return attn_simt_bwd(act_dtype, qkv, o, d_o, (const float*)lse, dqkv, (float*)delta, B, T, H, hd, st);
+}

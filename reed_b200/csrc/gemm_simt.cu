@@ -1,0 +1,112 @@
+// fp32-accurate SIMT GEMM with the shared epilogues.  This is the compute path of the fp32 precision mode
+// (parity bar 1e-5 relative; tcgen05 has no true-fp32 MMA) and of shapes the tcgen05 kernel does not take
+// (dimensions that are not multiples of 8).  D[M,N] = epi(A[M,K] . B[N,K]^T), generic element strides.
+#include "common.cuh"
+
+namespace reed {
+
+constexpr int SBM = 64, SBN = 64, SBK = 16;
+
+template <typename TA, typename TD>
+__global__ void __launch_bounds__(256) gemm_simt_kernel(const TA* __restrict__ A, int64_t a_sm, int64_t a_sk,
+                                                         const TA* __restrict__ B, int64_t b_sn, int64_t b_sk,
+                                                         TD* __restrict__ D, int64_t ldd, int M, int N, int K,
+                                                         EpiParams ep, int k_per_split) {
+  __shared__ float As[SBK][SBM + 4];
+  __shared__ float Bs[SBK][SBN + 4];
+  const int tid = threadIdx.x;
+  const int m0 = blockIdx.y * SBM, n0 = blockIdx.x * SBN;
+  const int tx = tid & 15, ty = tid >> 4;     // 16x16 threads, 4x4 outputs each
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  // loader mapping: choose the fastest-varying thread index along the contiguous dimension of each operand
+  const bool a_k_contig = a_sk == 1, b_k_contig = b_sk == 1;
+  // split-K (gridDim.z > 1): each z-slice reduces its own k-range and atomically adds into a zeroed fp32 D
+  const int k_begin = blockIdx.z * k_per_split;
+  const int k_end = min(K, k_begin + k_per_split);
+  for (int k0 = k_begin; k0 < k_end; k0 += SBK) {
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      int e = tid + it * 256;             // 1024 elements per tile
+      int mm, kk;
+      if (a_k_contig) { kk = e & 15; mm = e >> 4; } else { mm = e & 63; kk = e >> 6; }
+      int gm = m0 + mm, gk = k0 + kk;
+      As[kk][mm] = (gm < M && gk < k_end) ? to_f(A[gm * a_sm + gk * a_sk]) : 0.f;
+      int nn;
+      if (b_k_contig) { kk = e & 15; nn = e >> 4; } else { nn = e & 63; kk = e >> 6; }
+      int gn = n0 + nn;
+      gk = k0 + kk;
+      Bs[kk][nn] = (gn < N && gk < k_end) ? to_f(B[gn * b_sn + gk * b_sk]) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < SBK; ++kk) {
+      float a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = As[kk][ty * 4 + i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = Bs[kk][tx * 4 + j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+  const int col = n0 + tx * 4;
+  if (col >= N) return;   // N % 4 == 0 is required by the host wrapper
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    int row = m0 + ty * 4 + i;
+    if (row >= M) continue;
+    if (gridDim.z > 1) {
+      if constexpr (sizeof(TD) == 4) {
+        float* d = reinterpret_cast<float*>(D) + (int64_t)row * ldd + col;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float v = acc[i][j];
+          if (blockIdx.z == 0 && ep.bias != nullptr) v += ep.bias[col + j];
+          atomicAdd(d + j, v);
+        }
+      }
+    } else {
+      epilogue_store4<TD, TA>(ep, D, ldd, row, col, F4{{acc[i][0], acc[i][1], acc[i][2], acc[i][3]}});
+    }
+  }
+}
+
+int gemm_simt(int act_dtype, const void* A, int64_t lda, int a_mn, const void* B, int64_t ldb, int b_mn, void* D,
+              int64_t ldd, int d_dtype, int M, int N, int K, const EpiParams& ep, cudaStream_t st) {
+  REED_REQUIRE(N % 4 == 0 && ldd % 4 == 0, "gemm_simt needs N %% 4 == 0 and ldd %% 4 == 0 (N=%d ldd=%lld)", N, (long long)ldd);
+  dim3 grid(ceil_div(N, SBN), ceil_div(M, SBM));
+  int k_per_split = K > 0 ? K : 1;
+  // few output tiles and a long reduction (patch-embed / final-layer wgrad): split K across the machine
+  const int tiles = grid.x * grid.y;
+  if (ep.kind == kEpiNone && d_dtype == kF32 && tiles * 2 <= kNumSMs && K >= 2048) {
+    int splits = (2 * kNumSMs) / tiles;
+    int max_splits = K / 256;
+    if (splits > max_splits) splits = max_splits;
+    if (splits > 1) {
+      k_per_split = ceil_div(ceil_div(K, splits), SBK) * SBK;
+      grid.z = ceil_div(K, k_per_split);
+      if (!ep.accumulate)
+        REED_CHECK_CUDA(cudaMemset2DAsync(D, (size_t)ldd * 4, 0, (size_t)N * 4, (size_t)M, st));
+    }
+  }
+  int64_t a_sm = a_mn ? 1 : lda, a_sk = a_mn ? lda : 1;
+  int64_t b_sn = b_mn ? 1 : ldb, b_sk = b_mn ? ldb : 1;
+#define GS(TA, TD) gemm_simt_kernel<TA, TD><<<grid, 256, 0, st>>>((const TA*)A, a_sm, a_sk, (const TA*)B, b_sn, b_sk, (TD*)D, ldd, M, N, K, ep, k_per_split)
+  if (act_dtype == kF32 && d_dtype == kF32) GS(float, float);
+  else if (act_dtype == kBF16 && d_dtype == kBF16) GS(bf16, bf16);
+  else if (act_dtype == kBF16 && d_dtype == kF32) GS(bf16, float);
+  else return fail("gemm_simt: fp32 activations with bf16 output are not a supported combination");
+#undef GS
+  REED_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace reed

@@ -1,0 +1,233 @@
+"""Data-parallel train step for SiT + SILoss: the step glue of the reference ``image/train.py`` on flat buffers.
+
+Restates /root/reference/image/train.py:
+  * 220, 270      EMA = deepcopy(model), ``update_ema(ema, model, decay=0)`` at start
+  * 253-259       AdamW(lr 1e-4, betas (0.9, 0.999), wd 0, eps 1e-8)
+  * 396-398       loss = mean(denoising) * diffusion_decay + proj_loss * proj_coeff * repa_decay
+  * 401           backward; under DDP one gradient all-reduce (average) per step, bucketed, overlapped with backward
+  * 402-407       clip_grad_norm_(max_grad_norm)
+  * 408-412       optimizer.step(); zero_grad; update_ema(ema, model, 0.9999)   (EMA covers the frozen pos_embed too)
+
+B200 design: parameters, gradients, Adam moments, EMA weights and the bf16 GEMM shadows live in flat per-bucket
+buffers (one bucket per transformer block + one for embedders/projectors/final layer).  Weight-gradient GEMMs write
+straight into the flat gradient (no autograd accumulation pass); each block's bucket is all-reduced over NCCL
+(NVLink 5 / NVSwitch) as soon as that block's backward finishes, on NCCL's own stream, overlapping the remaining
+backward; the optimizer tail is one norm pass + one fused clip/AdamW/EMA/shadow-refresh kernel per bucket.
+"""
+from __future__ import annotations
+
+import copy
+from typing import Dict, List, Optional
+
+import torch
+import torch.distributed as dist
+import torch.nn as nn
+
+from .. import ops
+
+_ALIGN = 8     # elements; keeps every parameter's bf16 shadow 16-byte aligned for TMA
+
+
+class Bucket:
+    def __init__(self, name: str):
+        self.name = name
+        self.params: List[nn.Parameter] = []
+        self.names: List[str] = []
+        self.offsets: List[int] = []
+        self.numel = 0
+        self.work = None
+
+    def add(self, name, p):
+        self.names.append(name)
+        self.params.append(p)
+        self.offsets.append(self.numel)
+        self.numel += (p.numel() + _ALIGN - 1) // _ALIGN * _ALIGN
+
+
+class FlatState:
+    """Re-homes a model's parameters into flat per-bucket storage (works on any device; kernels need CUDA)."""
+
+    def __init__(self, model: nn.Module, ema: Optional[nn.Module] = None, with_shadow: bool = True):
+        self.model = model
+        self.ema = ema
+        self.buckets: List[Bucket] = []
+        self.frozen: List[tuple] = []          # (param, ema_param) for requires_grad=False parameters
+        ema_params = dict(ema.named_parameters()) if ema is not None else {}
+        by_key: Dict[str, Bucket] = {}
+
+        def bucket_for(name):
+            key = ".".join(name.split(".")[:2]) if name.startswith("blocks.") else "outer"
+            if key not in by_key:
+                by_key[key] = Bucket(key)
+                self.buckets.append(by_key[key])
+            return by_key[key]
+
+        for name, p in model.named_parameters():
+            if not p.requires_grad:
+                self.frozen.append((p, ema_params.get(name)))
+                continue
+            bucket_for(name).add(name, p)
+
+        for b in self.buckets:
+            dev = b.params[0].device
+            b.param = torch.zeros(b.numel, device=dev, dtype=torch.float32)
+            b.grad = torch.zeros(b.numel, device=dev, dtype=torch.float32)
+            b.exp_avg = torch.zeros(b.numel, device=dev, dtype=torch.float32)
+            b.exp_avg_sq = torch.zeros(b.numel, device=dev, dtype=torch.float32)
+            b.ema = torch.zeros(b.numel, device=dev, dtype=torch.float32) if ema is not None else None
+            b.shadow = torch.zeros(b.numel, device=dev, dtype=torch.bfloat16) if with_shadow else None
+            for name, p, off in zip(b.names, b.params, b.offsets):
+                n = p.numel()
+                view = b.param[off:off + n].view(p.shape)
+                view.copy_(p.data)
+                p.data = view
+                gview = b.grad[off:off + n].view(p.shape)
+                p.grad = gview
+                # nn.Embedding gradients arrive through autograd (dense add into p.grad); everything else is
+                # written by the wgrad / bias-gradient kernels directly
+                p._reed_kernel_grad = not name.endswith("embedding_table.weight")
+                if p._reed_kernel_grad:
+                    p._reed_main_grad = gview
+                    p._reed_grad_fresh = True
+                if with_shadow:
+                    sview = b.shadow[off:off + n].view(p.shape)
+                    sview.copy_(p.data)
+                    p._reed_shadow = sview
+                    p._reed_shadow_version = p._version
+                if ema is not None:
+                    ep = ema_params[name]
+                    eview = b.ema[off:off + n].view(p.shape)
+                    eview.copy_(p.data)                      # update_ema(ema, model, decay=0)
+                    ep.data = eview
+        for p, ep in self.frozen:
+            if ep is not None:
+                ep.data.copy_(p.data)
+        self._block_bucket = {b.name: b for b in self.buckets}
+
+    # -- gradient lifecycle ----------------------------------------------------------------------------------
+    def begin_step(self):
+        """Equivalent of optimizer.zero_grad(): kernel-written gradients are overwritten on their first write;
+        gradients that arrive through autograd (the label-embedding table) are zeroed and accumulated into."""
+        for b in self.buckets:
+            b.work = None
+            for p, off in zip(b.params, b.offsets):
+                if p._reed_kernel_grad:
+                    p._reed_grad_fresh = True
+                    p.grad = None
+                else:
+                    g = b.grad[off:off + p.numel()].view(p.shape)
+                    g.zero_()
+                    p.grad = g
+
+    def finish_backward(self):
+        """Zero the gradient of any kernel-written parameter the backward pass never touched; expose .grad views."""
+        for b in self.buckets:
+            for p, off in zip(b.params, b.offsets):
+                if p._reed_kernel_grad:
+                    if p._reed_grad_fresh:
+                        p._reed_main_grad.zero_()
+                    p.grad = p._reed_main_grad
+
+    def bucket_of_block(self, index: int) -> Optional[Bucket]:
+        return self._block_bucket.get(f"blocks.{index}")
+
+    def total_params(self):
+        return sum(sum(p.numel() for p in b.params) for b in self.buckets)
+
+
+class GradientReducer:
+    """Bucketed gradient all-reduce (sum; the 1/world factor is folded into the optimizer kernel)."""
+
+    def __init__(self, state: FlatState, group=None):
+        self.state = state
+        self.group = group
+        self.world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+
+    @property
+    def grad_scale(self):
+        return 1.0 / self.world
+
+    def launch(self, bucket: Bucket):
+        if self.world == 1 or bucket.work is not None:
+            return
+        bucket.work = dist.all_reduce(bucket.grad, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+
+    def finish(self):
+        for b in self.state.buckets:
+            self.launch(b)
+        for b in self.state.buckets:
+            if b.work is not None:
+                b.work.wait()
+                b.work = None
+
+
+class ReedTrainer:
+    """loss -> backward (+ overlapped all-reduce) -> clip -> AdamW -> EMA, one call per optimizer step."""
+
+    def __init__(self, model: nn.Module, loss_fn, *, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0,
+                 max_grad_norm=1.0, ema_decay=0.9999, proj_coeff=0.5, precision: Optional[str] = "bf16", group=None,
+                 with_ema=True):
+        self.model = model
+        self.loss_fn = loss_fn
+        self.lr, self.betas, self.eps, self.weight_decay = lr, betas, eps, weight_decay
+        self.max_grad_norm, self.ema_decay, self.proj_coeff = max_grad_norm, ema_decay, proj_coeff
+        if precision is not None:
+            model.reed_precision = precision
+        self.ema = None
+        if with_ema:
+            self.ema = copy.deepcopy(model)
+            for p in self.ema.parameters():
+                p.requires_grad_(False)
+            self.ema.eval()
+        self.state = FlatState(model, self.ema, with_shadow=True)
+        self.reducer = GradientReducer(self.state, group)
+        if self.reducer.world > 1:                      # DDP broadcasts rank 0's weights when it wraps the model
+            for b in self.state.buckets:
+                dist.broadcast(b.param, 0, group=group)
+                if b.ema is not None:
+                    b.ema.copy_(b.param)
+                if b.shadow is not None:
+                    b.shadow.copy_(b.param)
+        self.step_count = 0
+        dev = next(model.parameters()).device
+        self._norm_sq = torch.zeros(1, device=dev, dtype=torch.float64)
+        # all-reduce each block's bucket as soon as that block's backward has produced its last gradient
+        for i, blk in enumerate(model.blocks):
+            bucket = self.state.bucket_of_block(i)
+            blk._reed_after_backward = (lambda b=bucket: self.reducer.launch(b))
+
+    def compute_loss(self, images, labels, zs, diffusion_decay=1.0, repa_decay=1.0):
+        out = self.loss_fn(self.model, images, dict(y=labels), zs=zs)
+        loss = out["denoising_loss"].mean() * diffusion_decay + out["proj_loss"] * (self.proj_coeff * repa_decay)
+        return loss, out
+
+    def optimizer_step(self):
+        self.step_count += 1
+        st = torch.cuda.current_stream().cuda_stream
+        self._norm_sq.zero_()
+        for b in self.state.buckets:
+            ops._launch("reed_grad_sumsq", b.grad.data_ptr(), b.numel, self._norm_sq.data_ptr(), st)
+        clip = self.max_grad_norm is not None and self.max_grad_norm > 0
+        for b in self.state.buckets:
+            ops._launch("reed_adamw_ema", b.param.data_ptr(), b.grad.data_ptr(), b.exp_avg.data_ptr(),
+                        b.exp_avg_sq.data_ptr(), b.ema.data_ptr() if b.ema is not None else b.param.data_ptr(),
+                        b.shadow.data_ptr() if b.shadow is not None else None, b.numel,
+                        self._norm_sq.data_ptr() if clip else None, float(self.max_grad_norm or 0.0),
+                        self.reducer.grad_scale, self.lr, self.betas[0], self.betas[1], self.eps, self.weight_decay,
+                        self.step_count, self.ema_decay if b.ema is not None else 0.0, st)
+        for p, ep in self.state.frozen:
+            if ep is not None:
+                ops._launch("reed_ema_update", p.data_ptr(), ep.data_ptr(), p.numel(), self.ema_decay, st)
+
+    def grad_norm(self) -> torch.Tensor:
+        """Global gradient norm of the last step (device scalar, after the all-reduce average)."""
+        return (self._norm_sq.sqrt() * self.reducer.grad_scale).float()
+
+    def train_step(self, images, labels, zs, diffusion_decay=1.0, repa_decay=1.0):
+        self.state.begin_step()
+        loss, out = self.compute_loss(images, labels, zs, diffusion_decay, repa_decay)
+        loss.backward()
+        self.state.finish_backward()
+        self.reducer.finish()
+        self.optimizer_step()
+        return loss.detach(), out

@@ -1,0 +1,527 @@
+"""Tensor-level wrappers and autograd functions over the C-ABI kernels (libreed_sm100.so).
+
+PyTorch is plumbing here: device memory (caching allocator), streams, autograd bookkeeping.  Every arithmetic
+step of the hot path is one of the hand-written kernels; there is no PyTorch/CPU fallback.
+
+Precision modes (`act dtype`):
+  * torch.float32  - fp32 activations, SIMT fp32 GEMM/attention; parity bar 1e-5 relative.
+  * torch.bfloat16 - bf16 activations and GEMM operands (tcgen05, fp32 accumulate), fp32 residual stream,
+                     fp32 master weights with bf16 shadow copies; parity bar 2e-2 relative.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from . import _cabi
+from ._cabi import call
+
+F32, BF16 = 0, 1
+EPI_NONE, EPI_GELU, EPI_SILU, EPI_GATE_RES, EPI_DGELU, EPI_DSILU = range(6)
+ACT_NONE, ACT_GELU, ACT_SILU = 0, 1, 2
+BACKEND_AUTO, BACKEND_SIMT, BACKEND_TENSOR = 0, 1, 2
+
+_gemm_backend = BACKEND_AUTO
+_attn_backend = BACKEND_AUTO
+launch_count = 0     # kernels launched through this module (bench.py reports it as gpu_launches)
+
+
+def set_backends(gemm: int = BACKEND_AUTO, attention: int = BACKEND_AUTO):
+    """Test/debug knob: force the SIMT kernels or require the tensor-core kernels."""
+    global _gemm_backend, _attn_backend
+    _gemm_backend, _attn_backend = gemm, attention
+
+
+def _code(dtype: torch.dtype) -> int:
+    if dtype == torch.float32:
+        return F32
+    if dtype == torch.bfloat16:
+        return BF16
+    raise TypeError(f"reed_b200 kernels take float32 or bfloat16 tensors, got {dtype}")
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("reed_b200 runs on CUDA (sm_100a) tensors only; there is no CPU fallback")
+
+
+def _launch(name, *args, n=1):
+    global launch_count
+    launch_count += n
+    call(name, *args)
+
+
+# --------------------------------------------------------------------------------------------------
+# weights: fp32 master -> bf16 shadow
+# --------------------------------------------------------------------------------------------------
+
+def cast(x: torch.Tensor, dtype: torch.dtype, op: int = 0) -> torch.Tensor:
+    """dtype cast (op=0) or SiLU+cast (op=1) through reed_unary."""
+    if op == 0 and x.dtype == dtype:
+        return x
+    x = x.contiguous()
+    out = torch.empty_like(x, dtype=dtype)
+    n = x.numel()
+    if n % 4:
+        raise ValueError("reed_unary needs a multiple of 4 elements")
+    _launch("reed_unary", _p(x), _code(x.dtype), _p(out), _code(dtype), op, n, _stream())
+    return out
+
+
+def weight_for(p: torch.Tensor, act_dtype: torch.dtype) -> torch.Tensor:
+    """The tensor the GEMM reads for parameter ``p``: the fp32 master, or its bf16 shadow (refreshed when stale)."""
+    w = p.detach()
+    if act_dtype == torch.float32:
+        return w
+    shadow = getattr(p, "_reed_shadow", None)
+    if shadow is not None and getattr(p, "_reed_shadow_version", -1) == p._version and shadow.device == p.device:
+        return shadow
+    w = w.contiguous()
+    if shadow is None or shadow.shape != w.shape or shadow.device != w.device:
+        shadow = torch.empty_like(w, dtype=torch.bfloat16)
+    _launch("reed_unary", _p(w), F32, _p(shadow), BF16, 0, w.numel(), _stream())
+    p._reed_shadow = shadow
+    p._reed_shadow_version = p._version
+    return shadow
+
+
+def _grad_target(p: torch.Tensor):
+    """(buffer, accumulate) when a trainer owns flat gradient storage for ``p`` (see trainer.FlatState)."""
+    main = getattr(p, "_reed_main_grad", None)
+    if main is None:
+        return None, False
+    fresh = getattr(p, "_reed_grad_fresh", True)
+    p._reed_grad_fresh = False
+    return main, not fresh
+
+
+# --------------------------------------------------------------------------------------------------
+# raw kernel wrappers
+# --------------------------------------------------------------------------------------------------
+
+def gemm(a, b, *, a_mn=False, b_mn=False, out=None, out_dtype=torch.float32, epilogue=EPI_NONE, bias=None, aux=None,
+         gate=None, rows_per_group=1, out2=None, accumulate=False):
+    """out[M,N] = epi(A . B^T).  ``a`` is [M,K] (or [K,M] when a_mn), ``b`` is [N,K] (or [K,N] when b_mn)."""
+    assert a.dim() == 2 and b.dim() == 2 and a.stride(1) == 1 and b.stride(1) == 1, "operands must be row-major 2-D"
+    assert a.dtype == b.dtype
+    M, K = (a.shape[1], a.shape[0]) if a_mn else (a.shape[0], a.shape[1])
+    N, Kb = (b.shape[1], b.shape[0]) if b_mn else (b.shape[0], b.shape[1])
+    assert K == Kb, f"contraction mismatch {K} vs {Kb}"
+    if out is None:
+        out = torch.empty((M, N), device=a.device, dtype=out_dtype)
+    assert out.shape == (M, N) and out.stride(1) == 1
+    _launch("reed_gemm", _code(a.dtype), _p(a), a.stride(0), int(a_mn), _p(b), b.stride(0), int(b_mn), _p(out),
+            out.stride(0), _code(out.dtype), M, N, K, epilogue, _p(bias), _p(aux), aux.stride(0) if aux is not None else 0,
+            _p(gate), gate.stride(0) if gate is not None else 0, rows_per_group, _p(out2),
+            out2.stride(0) if out2 is not None else 0, int(accumulate), _gemm_backend, _stream())
+    return out
+
+
+def colsum(src: torch.Tensor, out: torch.Tensor):
+    """out[n] += sum_m src[m, n]  (out fp32, pre-initialised)."""
+    M, N = src.shape
+    _launch("reed_colsum", _p(src), _code(src.dtype), src.stride(0), _p(out), M, N, _stream())
+
+
+def act_bwd(dy, h, act):
+    dy = dy.contiguous()
+    dx = torch.empty_like(dy)
+    _launch("reed_act_bwd", _p(dy), _code(dy.dtype), _p(h), _code(h.dtype), _p(dx), 1 if act == ACT_GELU else 2,
+            dy.numel(), _stream())
+    return dx
+
+
+def ln_modulate_fwd(x, shift, scale, rows_per_group, act_dtype, eps=1e-6):
+    M, D = x.shape
+    out = torch.empty((M, D), device=x.device, dtype=act_dtype)
+    mean = torch.empty((M,), device=x.device, dtype=torch.float32)
+    rstd = torch.empty((M,), device=x.device, dtype=torch.float32)
+    assert shift.stride(0) == scale.stride(0) and shift.stride(1) == 1 and scale.stride(1) == 1
+    _launch("reed_ln_modulate_fwd", _p(x), _p(shift), _p(scale), shift.stride(0), rows_per_group, _p(out),
+            _code(act_dtype), _p(mean), _p(rstd), M, D, eps, _stream())
+    return out, mean, rstd
+
+
+def ln_modulate_bwd(dout, x, mean, rstd, scale, rows_per_group, dres, dshift, dscale):
+    """Returns dx = dres + LN'(dout); accumulates into dshift/dscale (views with the same row stride as scale)."""
+    M, D = x.shape
+    dx = torch.empty_like(x)
+    assert dshift.stride(0) == scale.stride(0) == dscale.stride(0)
+    _launch("reed_ln_modulate_bwd", _p(dout), _code(dout.dtype), _p(x), _p(mean), _p(rstd), _p(scale), scale.stride(0),
+            rows_per_group, _p(dres), _p(dx), _p(dshift), _p(dscale), M, D, _stream())
+    return dx
+
+
+def gate_bwd(dxn, y, gate, rows_per_group, dgate, dbias):
+    M, D = dxn.shape
+    dy = torch.empty_like(y)
+    assert dgate.stride(0) == gate.stride(0)
+    _launch("reed_gate_bwd", _p(dxn), _p(y), _code(y.dtype), _p(gate), gate.stride(0), rows_per_group, _p(dy), _p(dgate),
+            _p(dbias), M, D, _stream())
+    return dy
+
+
+def attention_fwd(qkv, B, T, H, hd):
+    o = torch.empty((B * T, H * hd), device=qkv.device, dtype=qkv.dtype)
+    lse = torch.empty((B, H, T), device=qkv.device, dtype=torch.float32)
+    _launch("reed_attn_fwd", _code(qkv.dtype), _p(qkv), _p(o), _p(lse), B, T, H, hd, _attn_backend, _stream())
+    return o, lse
+
+
+def attention_bwd(qkv, o, d_o, lse, B, T, H, hd):
+    dqkv = torch.empty_like(qkv)
+    delta = torch.empty((B, H, T), device=qkv.device, dtype=torch.float32)
+    _launch("reed_attn_bwd", _code(qkv.dtype), _p(qkv), _p(o), _p(d_o), _p(lse), _p(dqkv), _p(delta), B, T, H, hd,
+            _attn_backend, _stream(), n=2)
+    return dqkv
+
+
+# --------------------------------------------------------------------------------------------------
+# autograd functions
+# --------------------------------------------------------------------------------------------------
+
+def _weight_grad(p, dy2d, x2d):
+    """dW[N,K] = dy^T x written into the trainer's flat gradient when present; returns what autograd should see."""
+    main, acc = _grad_target(p)
+    if main is not None:
+        gemm(dy2d, x2d, a_mn=True, b_mn=True, out=main.view(dy2d.shape[1], x2d.shape[1]), accumulate=acc)
+        return None
+    return gemm(dy2d, x2d, a_mn=True, b_mn=True, out_dtype=torch.float32).view(p.shape)
+
+
+def _bias_grad(p, dy2d):
+    if p is None:
+        return None
+    main, acc = _grad_target(p)
+    if main is not None:
+        if not acc:
+            main.zero_()
+        colsum(dy2d, main)
+        return None
+    out = torch.zeros(dy2d.shape[1], device=dy2d.device, dtype=torch.float32)
+    colsum(dy2d, out)
+    return out
+
+
+class LinearFn(torch.autograd.Function):
+    """y = act(x W^T + b).  x: [M,K] fp32 or act dtype; W: fp32 master [N,K]; output dtype selectable."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, act, act_dtype, out_dtype):
+        _require_cuda(x, weight)
+        x_in_dtype = x.dtype
+        xa = cast(x, act_dtype)
+        w2 = weight_for(weight, act_dtype).view(weight.shape[0], -1)
+        b = bias.detach() if bias is not None else None
+        if act == ACT_NONE:
+            y = gemm(xa, w2, out_dtype=out_dtype, bias=b)
+            h = None
+        else:
+            h = torch.empty((xa.shape[0], w2.shape[0]), device=x.device, dtype=act_dtype)
+            y = gemm(xa, w2, out_dtype=out_dtype, bias=b, epilogue=EPI_GELU if act == ACT_GELU else EPI_SILU, out2=h)
+        ctx.save_for_backward(xa, h)
+        ctx.params = (weight, bias)     # python objects: carry the shadow / flat-gradient attributes
+        ctx.act, ctx.act_dtype, ctx.x_in_dtype = act, act_dtype, x_in_dtype
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        xa, h = ctx.saved_tensors
+        weight, bias = ctx.params
+        act_dtype = ctx.act_dtype
+        dy = cast(dy.contiguous(), act_dtype)
+        if ctx.act != ACT_NONE:
+            dy = act_bwd(dy, h, ctx.act)
+        w2 = weight_for(weight, act_dtype).view(weight.shape[0], -1)
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = gemm(dy, w2, b_mn=True, out_dtype=ctx.x_in_dtype)
+        dw = _weight_grad(weight, dy, xa) if ctx.needs_input_grad[1] else None
+        db = _bias_grad(bias, dy) if (bias is not None and ctx.needs_input_grad[2]) else None
+        return dx, dw, db, None, None, None
+
+
+def linear(x, weight, bias, *, act=ACT_NONE, act_dtype, out_dtype=None):
+    return LinearFn.apply(x, weight, bias, act, act_dtype, out_dtype if out_dtype is not None else act_dtype)
+
+
+class SiluCastFn(torch.autograd.Function):
+    """silu(c) emitted in the act dtype (the shared input of every adaLN linear, sit.py:125-133,148-154)."""
+
+    @staticmethod
+    def forward(ctx, c, act_dtype):
+        _require_cuda(c)
+        ctx.save_for_backward(c)
+        return cast(c, act_dtype, op=1)
+
+    @staticmethod
+    def backward(ctx, dy):
+        (c,) = ctx.saved_tensors
+        return act_bwd(cast(dy.contiguous(), torch.float32), c, ACT_SILU), None
+
+
+class CastFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, dtype):
+        ctx.in_dtype = x.dtype
+        return cast(x, dtype)
+
+    @staticmethod
+    def backward(ctx, dy):
+        return cast(dy.contiguous(), ctx.in_dtype), None
+
+
+class TokenMeanFn(torch.autograd.Function):
+    """x.mean(dim=1) for the text projector (sit.py:292,301); fp32 in, act dtype out."""
+
+    @staticmethod
+    def forward(ctx, x, act_dtype):
+        _require_cuda(x)
+        B, T, D = x.shape
+        x = x.contiguous()
+        out = torch.empty((B, D), device=x.device, dtype=act_dtype)
+        _launch("reed_group_mean_fwd", _p(x), _p(out), _code(act_dtype), B, T, D, _stream())
+        ctx.shape = (B, T, D)
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        B, T, D = ctx.shape
+        dy = cast(dy.contiguous(), torch.float32)
+        dx = torch.empty((B, T, D), device=dy.device, dtype=torch.float32)
+        _launch("reed_group_mean_bwd", _p(dy), _p(dx), B, T, D, 0, _stream())
+        return dx, None
+
+
+class LNModulateFn(torch.autograd.Function):
+    """modulate(LayerNorm(x), shift, scale) with x [B,T,D] fp32, shift/scale [B,D] fp32 views (sit.py:26-27,153-155)."""
+
+    @staticmethod
+    def forward(ctx, x, shift, scale, act_dtype):
+        _require_cuda(x)
+        B, T, D = x.shape
+        x2 = x.contiguous().view(B * T, D)
+        if shift.stride(0) != scale.stride(0) or shift.stride(1) != 1 or scale.stride(1) != 1:
+            shift, scale = shift.contiguous(), scale.contiguous()
+        out, mean, rstd = ln_modulate_fwd(x2, shift, scale, T, act_dtype)
+        ctx.save_for_backward(x2, mean, rstd, scale)
+        ctx.dims = (B, T, D)
+        return out.view(B, T, D)
+
+    @staticmethod
+    def backward(ctx, dout):
+        x2, mean, rstd, scale = ctx.saved_tensors
+        B, T, D = ctx.dims
+        ld = scale.stride(0)
+        # gradient buffers laid out with the same row stride as the (possibly strided) scale view
+        buf = torch.zeros((2, B, ld), device=x2.device, dtype=torch.float32)
+        dshift, dscale = buf[0][:, :D], buf[1][:, :D]
+        dx = ln_modulate_bwd(dout.contiguous().view(B * T, D), x2, mean, rstd, scale, T, None, dshift, dscale)
+        return dx.view(B, T, D), dshift, dscale, None
+
+
+class SiTBlockFn(torch.autograd.Function):
+    """One adaLN-Zero transformer block (sit.py:125-137 + timm Attention/Mlp): 8 kernels forward, 21 backward.
+
+    x: [B,T,D] fp32 residual stream; c_act: [B,D] = silu(c) in the act dtype (shared by all blocks).
+    mod = c_act W_ada^T + b_ada = (shift_a, scale_a, gate_a, shift_m, scale_m, gate_m), fp32 [B,6D].
+    """
+
+    @staticmethod
+    def forward(ctx, x, c_act, w_ada, b_ada, w_qkv, b_qkv, w_proj, b_proj, w_fc1, b_fc1, w_fc2, b_fc2, num_heads,
+                act_dtype, after_backward):
+        _require_cuda(x, c_act)
+        B, T, D = x.shape
+        M = B * T
+        H, hd = num_heads, D // num_heads
+        x0 = x.contiguous().view(M, D)
+        c_act = c_act.contiguous()
+        W = lambda p: weight_for(p, act_dtype)
+
+        mod = gemm(c_act, W(w_ada), out_dtype=torch.float32, bias=b_ada.detach())
+        sh_a, sc_a, g_a, sh_m, sc_m, g_m = (mod[:, i * D:(i + 1) * D] for i in range(6))
+        xm1, mean1, rstd1 = ln_modulate_fwd(x0, sh_a, sc_a, T, act_dtype)
+        qkv = gemm(xm1, W(w_qkv), out_dtype=act_dtype, bias=b_qkv.detach())
+        o, lse = attention_fwd(qkv, B, T, H, hd)
+        y1 = torch.empty((M, D), device=x.device, dtype=act_dtype)
+        x1 = gemm(o, W(w_proj), out_dtype=torch.float32, bias=b_proj.detach(), epilogue=EPI_GATE_RES, aux=x0, gate=g_a,
+                  rows_per_group=T, out2=y1)
+        xm2, mean2, rstd2 = ln_modulate_fwd(x1, sh_m, sc_m, T, act_dtype)
+        h = torch.empty((M, w_fc1.shape[0]), device=x.device, dtype=act_dtype)
+        a = gemm(xm2, W(w_fc1), out_dtype=act_dtype, bias=b_fc1.detach(), epilogue=EPI_GELU, out2=h)
+        y2 = torch.empty((M, D), device=x.device, dtype=act_dtype)
+        x2 = gemm(a, W(w_fc2), out_dtype=torch.float32, bias=b_fc2.detach(), epilogue=EPI_GATE_RES, aux=x1, gate=g_m,
+                  rows_per_group=T, out2=y2)
+
+        ctx.save_for_backward(x0, c_act, mod, mean1, rstd1, xm1, qkv, o, lse, y1, x1, mean2, rstd2, xm2, h, a, y2)
+        ctx.params = (w_ada, b_ada, w_qkv, b_qkv, w_proj, b_proj, w_fc1, b_fc1, w_fc2, b_fc2)
+        ctx.dims = (B, T, D, H, hd)
+        ctx.act_dtype = act_dtype
+        ctx.after_backward = after_backward
+        return x2.view(B, T, D)
+
+    @staticmethod
+    def backward(ctx, dx2):
+        x0, c_act, mod, mean1, rstd1, xm1, qkv, o, lse, y1, x1, mean2, rstd2, xm2, h, a, y2 = ctx.saved_tensors
+        w_ada, b_ada, w_qkv, b_qkv, w_proj, b_proj, w_fc1, b_fc1, w_fc2, b_fc2 = ctx.params
+        B, T, D, H, hd = ctx.dims
+        M = B * T
+        act_dtype = ctx.act_dtype
+        W = lambda p: weight_for(p, act_dtype)
+        dx2 = dx2.contiguous().view(M, D)
+        if dx2.dtype != torch.float32:
+            dx2 = cast(dx2, torch.float32)
+        sh_a, sc_a, g_a, sh_m, sc_m, g_m = (mod[:, i * D:(i + 1) * D] for i in range(6))
+        dmod = torch.zeros_like(mod)
+        dsh_a, dsc_a, dg_a, dsh_m, dsc_m, dg_m = (dmod[:, i * D:(i + 1) * D] for i in range(6))
+
+        def bias_buffer(p):
+            main, acc = _grad_target(p)
+            if main is not None:
+                if not acc:
+                    main.zero_()
+                return main, None
+            buf = torch.zeros(p.shape, device=p.device, dtype=torch.float32)
+            return buf, buf
+
+        # ---- MLP branch:  x2 = x1 + g_m * (gelu(xm2 W1^T + b1) W2^T + b2)
+        db2_buf, db2 = bias_buffer(b_fc2)
+        dy2 = gate_bwd(dx2, y2, g_m, T, dg_m, db2_buf)
+        dw2 = _weight_grad(w_fc2, dy2, a)
+        dh = gemm(dy2, W(w_fc2), b_mn=True, out_dtype=act_dtype, epilogue=EPI_DGELU, aux=h)
+        db1 = _bias_grad(b_fc1, dh)
+        dw1 = _weight_grad(w_fc1, dh, xm2)
+        dxm2 = gemm(dh, W(w_fc1), b_mn=True, out_dtype=act_dtype)
+        dx1 = ln_modulate_bwd(dxm2, x1, mean2, rstd2, sc_m, T, dx2, dsh_m, dsc_m)
+
+        # ---- attention branch:  x1 = x0 + g_a * (attn(xm1) Wp^T + bp)
+        dbp_buf, dbp = bias_buffer(b_proj)
+        dy1 = gate_bwd(dx1, y1, g_a, T, dg_a, dbp_buf)
+        dwp = _weight_grad(w_proj, dy1, o)
+        d_o = gemm(dy1, W(w_proj), b_mn=True, out_dtype=act_dtype)
+        dqkv = attention_bwd(qkv, o, d_o, lse, B, T, H, hd)
+        dbqkv = _bias_grad(b_qkv, dqkv)
+        dwqkv = _weight_grad(w_qkv, dqkv, xm1)
+        dxm1 = gemm(dqkv, W(w_qkv), b_mn=True, out_dtype=act_dtype)
+        dx0 = ln_modulate_bwd(dxm1, x0, mean1, rstd1, sc_a, T, dx1, dsh_a, dsc_a)
+
+        # ---- adaLN linear:  mod = c_act W_ada^T + b_ada
+        dmod_a = cast(dmod, act_dtype)
+        db_ada = _bias_grad(b_ada, dmod)
+        dw_ada = _weight_grad(w_ada, dmod_a, c_act)
+        dc = gemm(dmod_a, W(w_ada), b_mn=True, out_dtype=act_dtype) if ctx.needs_input_grad[1] else None
+
+        if ctx.after_backward is not None:
+            ctx.after_backward()
+        return (dx0.view(B, T, D), dc, dw_ada, db_ada, dwqkv, dbqkv, dwp, dbp, dw1, db1, dw2, db2, None, None, None)
+
+
+# --------------------------------------------------------------------------------------------------
+# SILoss pieces (loss.py:175-186, 204-225)
+# --------------------------------------------------------------------------------------------------
+
+def interpolate(x, eps, t, path_type):
+    """x_t = alpha_t x + sigma_t eps with per-sample t (no autograd: inputs are data)."""
+    _require_cuda(x, eps, t)
+    x, eps = x.contiguous(), eps.contiguous()
+    out = torch.empty_like(x)
+    B = x.shape[0]
+    _launch("reed_siloss_interp", _p(x), _p(eps), _p(t), _p(out), B, x.numel() // B, path_type, _stream())
+    return out
+
+
+class VelocityMSEFn(torch.autograd.Function):
+    """mean_flat((pred - (dalpha x + dsigma eps))^2) -> (B,)"""
+
+    @staticmethod
+    def forward(ctx, pred, x, eps, t, path_type):
+        _require_cuda(pred, x, eps, t)
+        pred = pred.contiguous()
+        B = pred.shape[0]
+        out = torch.empty((B,), device=pred.device, dtype=torch.float32)
+        _launch("reed_siloss_mse_fwd", _p(pred), _p(x), _p(eps), _p(t), _p(out), B, pred.numel() // B, path_type, _stream())
+        ctx.save_for_backward(pred, x, eps, t)
+        ctx.path_type = path_type
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        pred, x, eps, t = ctx.saved_tensors
+        B = pred.shape[0]
+        g = g.contiguous().float()
+        dpred = torch.empty_like(pred)
+        _launch("reed_siloss_mse_bwd", _p(pred), _p(x), _p(eps), _p(t), _p(g), _p(dpred), B, pred.numel() // B,
+                ctx.path_type, _stream())
+        return dpred, None, None, None, None
+
+
+class CosineAlignFn(torch.autograd.Function):
+    """-(normalize(z) . normalize(z~)).sum(-1).mean(-1) -> (B,);  z~: [B,T,Z] (grad), z: [B,T,Z] target."""
+
+    @staticmethod
+    def forward(ctx, zt, z):
+        _require_cuda(zt, z)
+        zt, z = zt.contiguous(), z.contiguous()
+        B, T, Z = zt.shape
+        stats = torch.empty((B * T, 3), device=zt.device, dtype=torch.float32)
+        align = torch.zeros((B,), device=zt.device, dtype=torch.float32)
+        _launch("reed_siloss_cos_fwd", _p(zt), _code(zt.dtype), _p(z), _code(z.dtype), _p(stats), _p(align), B, T, Z, _stream())
+        ctx.save_for_backward(zt, z, stats)
+        return align
+
+    @staticmethod
+    def backward(ctx, g):
+        zt, z, stats = ctx.saved_tensors
+        B, T, Z = zt.shape
+        g = g.contiguous().float()
+        dzt = torch.empty_like(zt)
+        _launch("reed_siloss_cos_bwd", _p(zt), _code(zt.dtype), _p(z), _code(z.dtype), _p(stats), _p(g), _p(dzt), B, T, Z,
+                _stream())
+        return dzt, None
+
+
+# --------------------------------------------------------------------------------------------------
+# sampler step (samplers.py:61-104, 124-187)
+# --------------------------------------------------------------------------------------------------
+
+def sampler_cast(x64, model_dtype, dup):
+    n = x64.numel()
+    shape = (x64.shape[0] * (2 if dup else 1),) + tuple(x64.shape[1:])
+    out = torch.empty(shape, device=x64.device, dtype=model_dtype)
+    _launch("reed_sampler_cast", _p(x64), _p(out), _code(model_dtype), n, int(dup), _stream())
+    return out
+
+
+def sampler_step(x_cur, v, *, eps=None, d_prev=None, want_slope=False, next_dup=None, guided=False, cfg=1.0, t_cur=0.0,
+                 dt=0.0, sde=False, path_type=0):
+    """One fused update.  Returns (x_next fp64, slope fp64 or None, next model input or None)."""
+    _require_cuda(x_cur, v)
+    n = x_cur.numel()
+    v = v.contiguous()
+    assert v.numel() == n * (2 if guided else 1)
+    x_next = torch.empty_like(x_cur)
+    slope = torch.empty_like(x_cur) if want_slope else None
+    x_model = None
+    if next_dup is not None:
+        shape = (x_cur.shape[0] * (2 if next_dup else 1),) + tuple(x_cur.shape[1:])
+        x_model = torch.empty(shape, device=x_cur.device, dtype=v.dtype)
+    _launch("reed_sampler_step", _p(x_cur), _p(v), _code(v.dtype), _p(eps), _p(d_prev), _p(slope), _p(x_next), _p(x_model),
+            n, int(guided), int(bool(next_dup)), int(sde), path_type, float(cfg), float(t_cur), float(dt), _stream())
+    return x_next, slope, x_model
+
+
+def device_check():
+    import ctypes
+    buf = ctypes.create_string_buffer(128)
+    call("reed_device_check", buf, 128)
+    return buf.value.decode()

@@ -1,0 +1,327 @@
+"""Kernel-level parity on the B200: every C-ABI kernel against a plain PyTorch fp32/fp64 restatement of the same op."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda"
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from reed_b200 import _cabi, ops as _ops
+    _cabi.load()
+    _ops.device_check()
+    yield _ops
+    _ops.set_backends()
+
+
+def _rel(a, b):
+    a, b = a.double(), b.double()
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+def _rand(*shape, dtype=torch.float32, scale=1.0, seed=None):
+    g = torch.Generator(device="cpu").manual_seed(seed if seed is not None else (hash(shape) % 1000))
+    return (torch.randn(*shape, generator=g) * scale).to(DEV).to(dtype)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# GEMM
+# ---------------------------------------------------------------------------------------------------------
+
+GEMM_SHAPES = [
+    # M, N, K
+    (256, 384, 128),       # aligned, small
+    (1000, 192, 320),      # ragged M
+    (128, 2304, 768),      # B/2 qkv
+    (512, 1152, 4608),     # XL fc2, long K
+    (77, 72 * 8, 200),     # ragged everything (N % 8 == 0)
+    (32, 6912, 1152),      # adaLN: M = batch
+    (4096, 768, 64),       # one k-block
+]
+
+
+def _operands(M, N, K, a_mn, b_mn, dtype):
+    a = _rand(M, K, dtype=dtype, seed=1)
+    b = _rand(N, K, dtype=dtype, scale=K ** -0.5, seed=2)
+    a_store = a.t().contiguous() if a_mn else a
+    b_store = b.t().contiguous() if b_mn else b
+    return a, b, a_store, b_store
+
+
+@pytest.mark.parametrize("layout", [(0, 0), (0, 1), (1, 1), (1, 0)])
+@pytest.mark.parametrize("shape", GEMM_SHAPES)
+def test_gemm_tcgen05_layouts(ops, shape, layout):
+    M, N, K = shape
+    a_mn, b_mn = layout
+    if (a_mn and M % 8) or (b_mn and N % 8) or (not a_mn and K % 8) or (not b_mn and K % 8):
+        pytest.skip("TMA needs 16-byte row pitches")
+    ops.set_backends(gemm=ops.BACKEND_TENSOR)
+    a, b, a_s, b_s = _operands(M, N, K, a_mn, b_mn, torch.bfloat16)
+    ref = a.float() @ b.float().t()
+    out = ops.gemm(a_s, b_s, a_mn=bool(a_mn), b_mn=bool(b_mn), out_dtype=torch.float32)
+    torch.cuda.synchronize()
+    assert _rel(out, ref) < 2e-5, (shape, layout)          # same bf16 inputs, fp32 accumulation
+    out_bf = ops.gemm(a_s, b_s, a_mn=bool(a_mn), b_mn=bool(b_mn), out_dtype=torch.bfloat16)
+    assert _rel(out_bf.float(), ref) < 1e-2
+
+
+@pytest.mark.parametrize("mode", ["fp32_simt", "bf16_simt", "bf16_tensor"])
+def test_gemm_epilogues(ops, mode):
+    dtype = torch.float32 if mode == "fp32_simt" else torch.bfloat16
+    ops.set_backends(gemm={"fp32_simt": ops.BACKEND_AUTO, "bf16_simt": ops.BACKEND_SIMT, "bf16_tensor": ops.BACKEND_TENSOR}[mode])
+    tol = 2e-5 if dtype == torch.float32 else 1.5e-2
+    B, T, N, K = 3, 64, 256, 192
+    M = B * T
+    a, w, _, _ = _operands(M, N, K, 0, 0, dtype)
+    bias = _rand(N, seed=3)
+    acc = a.float() @ w.float().t() + bias
+    # bias only, fp32 out; then accumulate on top
+    out = ops.gemm(a, w, out_dtype=torch.float32, bias=bias)
+    assert _rel(out, acc) < tol
+    ops.gemm(a, w, out=out, accumulate=True)
+    assert _rel(out, 2 * acc - bias) < tol
+    # GELU / SiLU with saved pre-activation
+    for epi, fn in ((ops.EPI_GELU, lambda v: F.gelu(v, approximate="tanh")), (ops.EPI_SILU, F.silu)):
+        h = torch.empty(M, N, device=DEV, dtype=dtype)
+        y = ops.gemm(a, w, out_dtype=dtype, bias=bias, epilogue=epi, out2=h)
+        assert _rel(h.float(), acc) < tol
+        assert _rel(y.float(), fn(h.float())) < tol
+    # gate * y + residual
+    res = _rand(M, N, seed=4)
+    mod = _rand(B, 3 * N, seed=5)
+    gate = mod[:, N:2 * N]
+    y2 = torch.empty(M, N, device=DEV, dtype=dtype)
+    x_new = ops.gemm(a, w, out_dtype=torch.float32, bias=bias, epilogue=ops.EPI_GATE_RES, aux=res, gate=gate,
+                     rows_per_group=T, out2=y2)
+    assert _rel(y2.float(), acc) < tol
+    want = res + gate.repeat_interleave(T, dim=0) * y2.float()
+    assert _rel(x_new, want) < 1e-5
+    # dgrad with activation derivative: D = (dy W) * act'(h)
+    dy = _rand(M, N, dtype=dtype, seed=6)
+    hsave = _rand(M, K, dtype=dtype, seed=7)
+    for epi, fn in ((ops.EPI_DGELU, lambda v: F.gelu(v, approximate="tanh")), (ops.EPI_DSILU, F.silu)):
+        hv = hsave.float().requires_grad_(True)
+        (grad,) = torch.autograd.grad(fn(hv).sum(), hv)
+        want = (dy.float() @ w.float()) * grad
+        got = ops.gemm(dy, w, b_mn=True, out_dtype=dtype, epilogue=epi, aux=hsave)
+        assert _rel(got.float(), want) < tol
+
+
+def test_gemm_simt_skinny_and_split_k(ops):
+    ops.set_backends()
+    # final-layer shapes: N = 16 forward, and its wgrad with a long reduction (split-K path)
+    M, D = 8192, 384
+    x = _rand(M, D, seed=1)
+    w = _rand(16, D, scale=D ** -0.5, seed=2)
+    out = ops.gemm(x, w, out_dtype=torch.float32)
+    assert _rel(out, x @ w.t()) < 2e-5
+    dy = _rand(M, 16, seed=3)
+    dw = ops.gemm(dy, x, a_mn=True, b_mn=True, out_dtype=torch.float32)
+    assert _rel(dw, dy.t() @ x) < 5e-5
+    prev = dw.clone()
+    ops.gemm(dy, x, a_mn=True, b_mn=True, out=dw, accumulate=True)
+    assert _rel(dw, 2 * prev) < 5e-5
+    xb, dyb = x.bfloat16(), dy.bfloat16()
+    dwb = ops.gemm(dyb, xb, a_mn=True, b_mn=True, out_dtype=torch.float32)
+    assert _rel(dwb, dyb.float().t() @ xb.float()) < 5e-5
+
+
+# ---------------------------------------------------------------------------------------------------------
+# LayerNorm + modulate, gate backward, small elementwise
+# ---------------------------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("D", [384, 768, 1152])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_ln_modulate_fwd_bwd(ops, D, dtype):
+    B, T = 3, 40
+    x = _rand(B * T, D, seed=1) * 2 + 0.3
+    mod = _rand(B, 6 * D, scale=0.3, seed=2)
+    shift, scale = mod[:, :D], mod[:, D:2 * D]
+    out, mean, rstd = ops.ln_modulate_fwd(x, shift, scale, T, dtype)
+    xr = x.clone().requires_grad_(True)
+    sh = shift.clone().requires_grad_(True)
+    sc = scale.clone().requires_grad_(True)
+    ref = F.layer_norm(xr, (D,), eps=1e-6).view(B, T, D) * (1 + sc[:, None]) + sh[:, None]
+    tol = 2e-6 if dtype == torch.float32 else 8e-3
+    assert _rel(out.float().view(B, T, D), ref) < tol
+    dout = _rand(B * T, D, dtype=dtype, seed=3)
+    dres = _rand(B * T, D, seed=4)
+    ref.backward(dout.float().view(B, T, D))
+    dmod = torch.zeros_like(mod)
+    dx = ops.ln_modulate_bwd(dout, x, mean, rstd, scale, T, dres, dmod[:, :D], dmod[:, D:2 * D])
+    assert _rel(dx, xr.grad + dres) < 2e-5
+    assert _rel(dmod[:, :D], sh.grad) < 2e-5
+    assert _rel(dmod[:, D:2 * D], sc.grad) < 2e-5
+    assert float(dmod[:, 2 * D:].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_gate_bwd_and_colsum(ops, dtype):
+    B, T, D = 4, 48, 768
+    dxn = _rand(B * T, D, seed=1)
+    y = _rand(B * T, D, dtype=dtype, seed=2)
+    mod = _rand(B, 6 * D, seed=3)
+    gate = mod[:, 2 * D:3 * D]
+    dmod = torch.zeros_like(mod)
+    dbias = torch.zeros(D, device=DEV)
+    dy = ops.gate_bwd(dxn, y, gate, T, dmod[:, 2 * D:3 * D], dbias)
+    want_dy = (dxn * gate.repeat_interleave(T, dim=0)).to(dtype)
+    assert _rel(dy.float(), want_dy.float()) < 1e-6 + (4e-3 if dtype == torch.bfloat16 else 0)
+    assert _rel(dmod[:, 2 * D:3 * D], (dxn * y.float()).view(B, T, D).sum(1)) < 2e-5
+    assert _rel(dbias, dy.float().sum(0)) < 2e-5
+    out = torch.zeros(D, device=DEV)
+    ops.colsum(y, out)
+    assert _rel(out, y.float().sum(0)) < 2e-5
+
+
+def test_unary_actbwd_tokenmean(ops):
+    x = _rand(6, 512, seed=1)
+    assert _rel(ops.cast(x, torch.bfloat16).float(), x.bfloat16().float()) == 0.0
+    assert _rel(ops.cast(x, torch.float32, op=1), F.silu(x)) < 1e-6
+    dy = _rand(6, 512, seed=2)
+    for act, fn in ((ops.ACT_GELU, lambda v: F.gelu(v, approximate="tanh")), (ops.ACT_SILU, F.silu)):
+        xv = x.clone().requires_grad_(True)
+        fn(xv).backward(dy)
+        assert _rel(ops.act_bwd(dy, x, act), xv.grad) < 2e-6
+    tok = _rand(3, 64, 256, seed=3).requires_grad_(True)
+    m = ops.TokenMeanFn.apply(tok, torch.float32)
+    assert _rel(m, tok.mean(1)) < 1e-6
+    m.backward(torch.ones_like(m))
+    assert _rel(tok.grad, torch.full_like(tok, 1 / 64)) < 1e-6
+
+
+# ---------------------------------------------------------------------------------------------------------
+# attention
+# ---------------------------------------------------------------------------------------------------------
+
+def _attention_reference(qkv, B, T, H, hd):
+    q, k, v = qkv.view(B, T, 3, H, hd).permute(2, 0, 3, 1, 4)
+    p = torch.softmax(q @ k.transpose(-1, -2) * hd ** -0.5, dim=-1)
+    return (p @ v).transpose(1, 2).reshape(B * T, H * hd)
+
+
+@pytest.mark.parametrize("cfg", [(2, 256, 3, 64), (2, 64, 2, 72), (1, 1024, 2, 72)])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_attention_fwd_bwd(ops, cfg, dtype):
+    B, T, H, hd = cfg
+    ops.set_backends()
+    qkv = _rand(B * T, 3 * H * hd, dtype=dtype, seed=1)
+    o, lse = ops.attention_fwd(qkv, B, T, H, hd)
+    ref_in = qkv.float().requires_grad_(True)
+    ref = _attention_reference(ref_in, B, T, H, hd)
+    tol = 3e-6 if dtype == torch.float32 else 1.2e-2
+    assert _rel(o.float(), ref) < tol
+    d_o = _rand(B * T, H * hd, dtype=dtype, seed=2)
+    ref.backward(d_o.float())
+    dqkv = ops.attention_bwd(qkv, o, d_o, lse, B, T, H, hd)
+    assert _rel(dqkv.float(), ref_in.grad) < (2e-5 if dtype == torch.float32 else 2e-2)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# SILoss kernels
+# ---------------------------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("path", [0, 1])
+def test_siloss_interp_and_mse(ops, path):
+    B = 5
+    x, eps, pred = _rand(B, 4, 32, 32, seed=1), _rand(B, 4, 32, 32, seed=2), _rand(B, 4, 32, 32, seed=3)
+    t = torch.rand(B, device=DEV)
+    tb = t.view(B, 1, 1, 1)
+    if path == 0:
+        a, s, da, ds = 1 - tb, tb, -1.0, 1.0
+    else:
+        a, s = torch.cos(tb * math.pi / 2), torch.sin(tb * math.pi / 2)
+        da, ds = -math.pi / 2 * torch.sin(tb * math.pi / 2), math.pi / 2 * torch.cos(tb * math.pi / 2)
+    assert _rel(ops.interpolate(x, eps, t, path), a * x + s * eps) < 2e-6
+    pr = pred.clone().requires_grad_(True)
+    ref = ((pr - (da * x + ds * eps)) ** 2).flatten(1).mean(1)
+    pg = pred.clone().requires_grad_(True)
+    got = ops.VelocityMSEFn.apply(pg, x, eps, t, path)
+    assert _rel(got, ref) < 2e-6
+    w = torch.rand(B, device=DEV)
+    (ref * w).sum().backward()
+    (got * w).sum().backward()
+    assert _rel(pg.grad, pr.grad) < 2e-6
+
+
+@pytest.mark.parametrize("dt_pair", [(torch.float32, torch.float32), (torch.bfloat16, torch.float32),
+                                     (torch.bfloat16, torch.bfloat16), (torch.float32, torch.bfloat16)])
+@pytest.mark.parametrize("shape", [(4, 256, 768), (3, 1, 3584)])
+def test_siloss_cosine(ops, shape, dt_pair):
+    B, T, Z = shape
+    zt = _rand(B, T, Z, dtype=dt_pair[0], seed=1)
+    z = _rand(B, T, Z, dtype=dt_pair[1], seed=2)
+    zr = zt.float().requires_grad_(True)
+    ref = -(F.normalize(z.float(), dim=-1) * F.normalize(zr, dim=-1)).sum(-1).mean(-1)
+    zg = zt.clone().requires_grad_(True)
+    got = ops.CosineAlignFn.apply(zg, z)
+    assert _rel(got, ref) < 5e-6
+    w = torch.rand(B, device=DEV)
+    (ref * w).sum().backward()
+    (got * w).sum().backward()
+    assert _rel(zg.grad.float(), zr.grad) < (2e-5 if dt_pair[0] == torch.float32 else 8e-3)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# sampler step, optimizer
+# ---------------------------------------------------------------------------------------------------------
+
+def test_sampler_step_formulas(ops):
+    n = 3
+    x = torch.randn(n, 4, 16, 16, device=DEV, dtype=torch.float64)
+    v = torch.randn(2 * n, 4, 16, 16, device=DEV)
+    eps = torch.randn_like(x)
+    t, dt, cfg = 0.7, -0.05, 1.8
+    # ODE, guided
+    xn, slope, xm = ops.sampler_step(x, v, want_slope=True, next_dup=True, guided=True, cfg=cfg, t_cur=t, dt=dt)
+    d = v.double()
+    d = d[n:] + cfg * (d[:n] - d[n:])
+    assert _rel(xn, x + dt * d) < 1e-14 and _rel(slope, d) < 1e-14
+    assert torch.equal(xm[:n], xn.float()) and torch.equal(xm[n:], xn.float())
+    # Heun corrector
+    xh, _, _ = ops.sampler_step(x, v[:n], d_prev=slope, t_cur=t, dt=dt)
+    assert _rel(xh, x + dt * (0.5 * slope + 0.5 * v[:n].double())) < 1e-14
+    # SDE, both paths
+    for path, name in ((0, "linear"), (1, "cosine")):
+        from oracle.samplers_oracle import score_from_velocity
+        tin = torch.full((2 * n,), t, dtype=torch.float64, device=DEV)
+        vv = v.double()
+        s = score_from_velocity(vv, torch.cat([x, x]), tin, name)
+        dd = vv - 0.5 * (2 * t) * s
+        dd = dd[n:] + cfg * (dd[:n] - dd[n:])
+        want = x + dd * dt + math.sqrt(2 * t) * eps * math.sqrt(abs(dt))
+        got, _, _ = ops.sampler_step(x, v, eps=eps, guided=True, cfg=cfg, t_cur=t, dt=dt, sde=True, path_type=path)
+        assert _rel(got, want) < 1e-12, name
+
+
+def test_fused_adamw_ema_matches_torch(ops):
+    from reed_b200._cabi import call
+    n = 10007 * 4 + 3
+    g0 = torch.Generator().manual_seed(0)
+    p = torch.randn(n, generator=g0).to(DEV)
+    ref_p = torch.nn.Parameter(p.clone())
+    opt = torch.optim.AdamW([ref_p], lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01)
+    ema_ref = p.clone()
+    m, v, ema = torch.zeros_like(p), torch.zeros_like(p), p.clone()
+    shadow = torch.zeros(n, device=DEV, dtype=torch.bfloat16)
+    norm_sq = torch.zeros(1, device=DEV, dtype=torch.float64)
+    st = torch.cuda.current_stream().cuda_stream
+    for step in range(1, 4):
+        g = (torch.randn(n, generator=g0) * (5.0 if step == 2 else 0.001)).to(DEV)
+        ref_p.grad = g.clone()
+        total = torch.nn.utils.clip_grad_norm_([ref_p], 1.0)
+        opt.step()
+        ema_ref.mul_(0.99).add_(ref_p.data, alpha=0.01)
+        norm_sq.zero_()
+        call("reed_grad_sumsq", g.data_ptr(), n, norm_sq.data_ptr(), st)
+        assert _rel(norm_sq.sqrt().float(), total) < 1e-5
+        call("reed_adamw_ema", p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), ema.data_ptr(), shadow.data_ptr(),
+             n, norm_sq.data_ptr(), 1.0, 1.0, 1e-3, 0.9, 0.999, 1e-8, 0.01, step, 0.99, st)
+        assert float((p - ref_p.data).abs().max()) < 2e-6
+        assert float((ema - ema_ref).abs().max()) < 2e-6
+        assert torch.equal(shadow, p.bfloat16())

@@ -1,0 +1,276 @@
+"""Model-level parity on the B200: the CUDA path (through the drop-in Python API, i.e. through the C-ABI) against the
+CPU oracle and against the committed golden outputs of the unmodified reference.
+
+Bars (BASELINE.json north_star): fp32 losses <= 1e-5 relative, bf16 <= 2e-2 relative, per-parameter gradient cosine
+>= 0.999, sampler outputs <= 1e-3 max-abs in fp32.
+"""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import loss_oracle, samplers_oracle, sit_oracle, train_oracle
+from oracle.fixtures import random_batch, random_state
+from oracle.sit_oracle import ArchSpec
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _rel(a, b):
+    a, b = torch.as_tensor(a).detach().double().cpu(), torch.as_tensor(b).detach().double().cpu()
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+def _build(spec: ArchSpec, sd, precision):
+    from reed_b200.image.models.sit import SiT
+    kw = {k: getattr(spec, k) for k in ("input_size", "patch_size", "in_channels", "hidden_size", "decoder_hidden_size",
+                                        "depth", "num_heads", "mlp_ratio", "class_dropout_prob", "num_classes",
+                                        "encoder_depth", "encoder_depth_text", "projector_dim")}
+    m = SiT(path_type="linear", use_cfg=True, z_dims=list(spec.z_dims), z_types=list(spec.z_types), fused_attn=True,
+            qk_norm=spec.qk_norm, **kw)
+    m.load_state_dict(sd, strict=True)
+    m.reed_precision = precision
+    return m.to(DEV)
+
+
+class _Replay:
+    """Forces SILoss / the label embedder to use recorded random draws (t, noise, drop mask)."""
+
+    def __init__(self, loss_fn, model, t, noise, drop):
+        self.loss_fn, self.model, self.t, self.noise, self.drop = loss_fn, model, t, noise, drop
+
+    def __enter__(self):
+        self._st = self.loss_fn._sample_time
+        self._rl = torch.randn_like
+        self._td = self.model.y_embedder.token_drop
+        self.loss_fn._sample_time = lambda batch: self.t.clone()
+        noise = self.noise
+        torch.randn_like = lambda x, **kw: noise.to(device=x.device, dtype=x.dtype)
+        drop = self.drop
+        nc = self.model.y_embedder.num_classes
+        self.model.y_embedder.token_drop = lambda labels, force=None: torch.where(drop.to(labels.device), nc, labels)
+        return self
+
+    def __exit__(self, *exc):
+        self.loss_fn._sample_time = self._st
+        torch.randn_like = self._rl
+        self.model.y_embedder.token_drop = self._td
+
+
+def _run_case(case, precision):
+    from reed_b200.image.loss import SILoss
+    spec = ArchSpec(**case["spec"])
+    sd = random_state(spec, case["state_seed"])
+    data = random_batch(spec, case["batch"], case["batch_seed"])
+    model = _build(spec, sd, precision).train()
+    fn = SILoss(prediction="v", path_type=case["path_type"], weighting=case["weighting"], enc_names=case["enc_names"],
+                loss_weights=case["loss_weights"], time_schedule=case["time_schedule"], cutoffs=case["cutoffs"])
+    kwargs = dict(y=data["y"].to(DEV))
+    with _Replay(fn, model, case["t"], case["noise"], case["drop"]):
+        out = fn(model, data["x"].to(DEV), kwargs, zs=[z.to(DEV) for z in data["zs"]], save_projloss=True)
+    assert kwargs["inference"] is False                       # caller's dict is mutated, like loss.py:183
+    return spec, sd, data, model, out
+
+
+@pytest.mark.parametrize("name", ["loss_a.pt", "loss_b.pt"])
+@pytest.mark.parametrize("precision,loss_tol,cos_min", [("fp32", 1e-5, 0.99999), ("bf16", 2e-2, 0.999)])
+def test_loss_and_gradients_match_reference_golden(golden, name, precision, loss_tol, cos_min):
+    case = golden(name)
+    spec, sd, data, model, out = _run_case(case, precision)
+    assert out["denoising_loss"].shape == (case["batch"],) and out["proj_loss"].dim() == 0
+    assert _rel(out["denoising_loss"], case["denoising_loss"]) < loss_tol
+    assert _rel(out["proj_loss"], case["proj_loss"]) < loss_tol
+    assert _rel(out["img_proj_loss"], case["img_proj_loss"]) < loss_tol
+    if len(case["enc_names"]) > 1:
+        assert _rel(out["text_proj_loss"], case["text_proj_loss"]) < loss_tol
+        assert _rel(out["loss_saver"]["text"], case["saver_text"]) < loss_tol
+    else:
+        assert out["text_proj_loss"] == 0.0 and isinstance(out["text_proj_loss"], float)
+    assert _rel(out["loss_saver"]["image"], case["saver_image"]) < loss_tol
+    total = out["denoising_loss"].mean() + case["proj_coeff"] * out["proj_loss"]
+    total.backward()
+    got = {n: p.grad for n, p in model.named_parameters() if p.grad is not None}
+    assert set(got) == set(case["grads"])
+    worst = 1.0
+    for k, g in case["grads"].items():
+        cos = float(F.cosine_similarity(got[k].flatten().double().cpu(), g.flatten().double(), dim=0))
+        worst = min(worst, cos)
+        assert cos >= cos_min, (k, cos)
+        if precision == "fp32":
+            assert _rel(got[k], g) < 2e-4, k
+    print(f"{name} {precision}: worst per-parameter gradient cosine {worst:.6f}")
+    # plain inference forward
+    model.eval()
+    with torch.no_grad():
+        t = case["t"]
+        x_t = ((1 - t) * data["x"] + t * case["noise"]).to(DEV)
+        pred, zs = model(x_t, t.flatten().to(DEV), y=data["y"].to(DEV))
+    assert zs is None and pred.shape == data["x"].shape
+    assert _rel(pred, case["eval_pred"]) < (2e-5 if precision == "fp32" else 3e-2)
+
+
+def test_time_schedules_broadcast_quirk(golden):
+    for schedule, case in golden("loss_c_schedules.pt").items():
+        case = dict(case)
+        spec = dict(case["spec"])
+        if spec["qk_norm"]:
+            # the golden case has qk_norm=True (covered by the oracle test); the CUDA path is checked on the
+            # projection-loss arithmetic only, which does not depend on the network internals being identical
+            continue
+    # direct check of the quirk on device with an analytic stand-in for the model
+    from reed_b200.image.loss import SILoss
+    B = 6
+    fn = SILoss(enc_names=["mocov3"], loss_weights={"mocov3": 0.7}, time_schedule="cosine")
+    z = torch.randn(B, 16, 32, device=DEV)
+    zt = torch.randn(B, 16, 32, device=DEV)
+
+    def fake_model(x, t, y=None, inference=True):
+        return torch.zeros_like(x), [zt]
+    torch.manual_seed(3)
+    out = fn(fake_model, torch.randn(B, 4, 8, 8, device=DEV), dict(y=None), zs=[z])
+    torch.manual_seed(3)
+    t = torch.rand(B, 1, 1, 1)
+    align = -(F.normalize(z, dim=-1) * F.normalize(zt, dim=-1)).sum(-1).mean(-1).cpu()
+    w = loss_oracle.schedule_weight(t, 0.7, "cosine").flatten()
+    assert _rel(out["proj_loss"], align.mean() * w.mean()) < 1e-5
+    assert _rel(out["proj_loss"], (align * w).mean()) > 1e-4
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-5), ("bf16", 2e-2)])
+def test_public_api_rng_order_matches_oracle(precision, tol):
+    """Seeded call through SILoss.__call__ (no replay hooks): t from the CPU generator, noise then label-drop from the
+    CUDA generator, in the reference's order."""
+    from reed_b200.image.loss import SILoss
+    spec = ArchSpec(input_size=32, hidden_size=384, decoder_hidden_size=384, depth=3, num_heads=6, encoder_depth=2,
+                    z_dims=[768], z_types=["i"], class_dropout_prob=0.5)
+    sd = random_state(spec, 11)
+    data = random_batch(spec, 8, 12)
+    model = _build(spec, sd, precision).train()
+    fn = SILoss(enc_names=["dinov2"], loss_weights={"dinov2": 1.0})
+    x = data["x"].to(DEV)
+    torch.manual_seed(2024)
+    out = fn(model, x, dict(y=data["y"].to(DEV)), zs=[data["zs"][0].to(DEV)])
+    torch.manual_seed(2024)
+    t = torch.rand((8, 1, 1, 1))
+    noise = torch.randn_like(x).cpu()
+    drop = (torch.rand(8, device=DEV) < 0.5).cpu()
+    assert 0 < int(drop.sum()) < 8
+    ref = loss_oracle.si_loss(sit_oracle.as_model(sd, spec, training=True, drop_mask=drop), data["x"], t, noise,
+                              data["zs"], enc_names=["dinov2"], loss_weights={"dinov2": 1.0},
+                              model_kwargs=dict(y=data["y"]))
+    assert _rel(out["denoising_loss"], ref["denoising_loss"]) < tol
+    assert _rel(out["proj_loss"], ref["proj_loss"]) < tol
+
+
+def test_samplers_match_reference_golden(golden):
+    from reed_b200.image.samplers import euler_maruyama_sampler, euler_sampler
+    fx = golden("samplers_a.pt")
+    spec = ArchSpec(**fx["spec"])
+    model = _build(spec, random_state(spec, fx["state_seed"]), "fp32").eval()
+    z, y = fx["latents"].to(DEV), fx["y"].to(DEV)
+    real_randn_like = torch.randn_like
+    for name, v in fx["variants"].items():
+        kw = v["kwargs"]
+        if v["sde"]:
+            it = iter(v["noises"])
+            torch.randn_like = lambda x, **k: next(it).to(x.device)
+            try:
+                res = euler_maruyama_sampler(model, z, y, **kw)
+            finally:
+                torch.randn_like = real_randn_like
+        else:
+            res = euler_sampler(model, z, y, **kw)
+        assert res.dtype == torch.float64 and res.is_cuda
+        err = float((res.cpu() - v["result"]).abs().max())
+        print(f"sampler {name}: max-abs err {err:.2e}")
+        assert err < 1e-3, name
+
+
+def test_sde_sampler_draws_fp64_normals_in_reference_order():
+    from reed_b200.image.samplers import euler_maruyama_sampler
+    spec = ArchSpec(input_size=16, hidden_size=128, decoder_hidden_size=128, depth=2, num_heads=2, encoder_depth=1,
+                    z_dims=[64], projector_dim=128)
+    sd = random_state(spec, 5)
+    model = _build(spec, sd, "fp32").eval()
+    z = torch.randn(2, 4, 16, 16, device=DEV)
+    y = torch.tensor([1, 2], device=DEV)
+    torch.manual_seed(9)
+    res = euler_maruyama_sampler(model, z, y, num_steps=4)
+    torch.manual_seed(9)
+    noises = [torch.randn_like(z.double()).cpu() for _ in range(3)]
+    ref = samplers_oracle.euler_maruyama(sit_oracle.as_model(sd, spec), z.cpu(), y.cpu(), num_steps=4, noises=noises)
+    assert float((res.cpu() - ref).abs().max()) < 1e-3
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_trainer_step_matches_reference_glue(golden, precision):
+    """clip -> AdamW -> EMA on flat buffers vs the golden produced with torch.optim.AdamW + reference update_ema."""
+    from reed_b200.image.loss import SILoss
+    from reed_b200.image.trainer import ReedTrainer
+    fx = golden("train_glue.pt")
+    spec = ArchSpec(**fx["spec"])
+    sd = random_state(spec, fx["state_seed"])
+    model = _build(spec, sd, precision).train()
+    fn = SILoss(enc_names=["dinov2"], loss_weights={"dinov2": 1.0})
+    tr = ReedTrainer(model, fn, precision=precision)
+    assert [n for n, _ in tr.ema.named_parameters()] == [n for n, _ in model.named_parameters()]
+    for rec in fx["steps"]:
+        data = random_batch(spec, 3, rec["batch_seed"])
+        with _Replay(fn, model, rec["t"], rec["noise"], rec["drop"]):
+            tr.state.begin_step()
+            loss, _ = tr.compute_loss(data["x"].to(DEV), data["y"].to(DEV), [z.to(DEV) for z in data["zs"]])
+            loss = loss * rec["scale"]
+            loss.backward()
+            tr.state.finish_backward()
+            tr.reducer.finish()
+            tr.optimizer_step()
+        tol = 1e-5 if precision == "fp32" else 2e-2
+        assert _rel(loss, rec["loss"]) < tol
+        assert _rel(tr.grad_norm(), rec["grad_norm"]) < (1e-4 if precision == "fp32" else 3e-2)
+    if precision == "fp32":
+        got, got_ema = model.state_dict(), tr.ema.state_dict()
+        for k in fx["final_model"]:
+            assert float((got[k].cpu() - fx["final_model"][k]).abs().max()) < 1e-5, k
+            assert float((got_ema[k].cpu() - fx["final_ema"][k]).abs().max()) < 1e-5, k
+    # shadows track the masters
+    for b in tr.state.buckets:
+        assert torch.equal(b.shadow, b.param.bfloat16())
+
+
+def test_full_size_properties_xl2_bf16():
+    """BASELINE config 3 shapes (SiT-XL/2, T=256, head_dim 72) at a small batch: size-independent properties."""
+    from reed_b200.image.loss import SILoss
+    from reed_b200.image.models.sit import SiT_models
+    torch.manual_seed(0)
+    model = SiT_models["SiT-XL/2"](input_size=32, num_classes=1000, use_cfg=True, z_dims=[768], z_types=["i"],
+                                   encoder_depth=8, fused_attn=True, qk_norm=False).to(DEV).train()
+    model.reed_precision = "bf16"
+    fn = SILoss(enc_names=["dinov2"], loss_weights={"dinov2": 1.0})
+    x = torch.randn(4, 4, 32, 32, device=DEV)
+    y = torch.randint(0, 1000, (4,), device=DEV)
+    zs = [torch.randn(4, 256, 768, device=DEV)]
+    # reference init: every gate is zero -> the network output is exactly 0 and denoising loss = mean(target^2)
+    torch.manual_seed(1)
+    out = fn(model, x, dict(y=y), zs=zs)
+    torch.manual_seed(1)
+    t = torch.rand(4, 1, 1, 1).to(DEV)
+    noise = torch.randn_like(x)
+    assert _rel(out["denoising_loss"], ((noise - x) ** 2).flatten(1).mean(1)) < 1e-5
+    assert -1.0 <= float(out["proj_loss"]) <= 1.0
+    (out["denoising_loss"].mean() + 0.5 * out["proj_loss"]).backward()
+    g = model.final_layer.linear.weight.grad
+    assert g is not None and torch.isfinite(g).all() and float(g.abs().max()) > 0
+    # gates are zero => blocks are the identity => adaLN/final-linear grads are the only non-zero block-side grads
+    assert float(model.blocks[20].attn.qkv.weight.grad.abs().max()) == 0.0
+    # batch-permutation equivariance of the model at inference
+    model.eval()
+    with torch.no_grad():
+        for lin in [b.adaLN_modulation[1] for b in model.blocks] + [model.final_layer.adaLN_modulation[1], model.final_layer.linear]:
+            lin.weight.normal_(0, 0.02)
+            lin.bias.normal_(0, 0.02)
+        tt = torch.rand(4, device=DEV)
+        p1, _ = model(x, tt, y=y)
+        perm = torch.tensor([2, 0, 3, 1], device=DEV)
+        p2, _ = model(x[perm], tt[perm], y=y[perm])
+    assert torch.isfinite(p1).all()
+    assert float((p1[perm] - p2).abs().max()) < 1e-5 * max(1.0, float(p1.abs().max()))
