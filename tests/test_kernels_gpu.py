@@ -20,7 +20,7 @@ def ops():
 
 
 def _rel(a, b):
-    a, b = a.double(), b.double()
+    a, b = a.detach().double(), b.detach().double()
     return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
 
 
@@ -256,9 +256,9 @@ def test_siloss_cosine(ops, shape, dt_pair):
     B, T, Z = shape
     zt = _rand(B, T, Z, dtype=dt_pair[0], seed=1)
     z = _rand(B, T, Z, dtype=dt_pair[1], seed=2)
-    zr = zt.float().requires_grad_(True)
+    zr = zt.detach().float().clone().requires_grad_(True)
     ref = -(F.normalize(z.float(), dim=-1) * F.normalize(zr, dim=-1)).sum(-1).mean(-1)
-    zg = zt.clone().requires_grad_(True)
+    zg = zt.detach().clone().requires_grad_(True)
     got = ops.CosineAlignFn.apply(zg, z)
     assert _rel(got, ref) < 5e-6
     w = torch.rand(B, device=DEV)
