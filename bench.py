@@ -147,12 +147,43 @@ class ClockSampler(threading.Thread):
                 "power_w_max": max(float(s[2]) for s in self.samples), "reasons": reasons, "samples": len(self.samples)}
 
 
-def run_gpu_arm(args, cfg):
-    import torch.distributed as dist
-    from reed_b200 import _cabi, ops
+def build_trainer(cfg, dev, precision="bf16"):
+    """Model (reference init, zero-init layers perturbed), SILoss and the flat-buffer trainer for one config."""
     from reed_b200.image.loss import SILoss
     from reed_b200.image.models.sit import SiT_models
     from reed_b200.image.trainer import ReedTrainer
+    spec = spec_for(cfg)
+    torch.manual_seed(0)          # same init on every rank; the trainer also broadcasts rank 0's weights
+    model = SiT_models[cfg["model"]](input_size=cfg["input_size"], num_classes=1000, use_cfg=True, z_dims=cfg["z_dims"],
+                                     z_types=cfg["z_types"], encoder_depth=cfg["encoder_depth"],
+                                     encoder_depth_text=cfg["encoder_depth_text"], fused_attn=True, qk_norm=False,
+                                     **cfg.get("extra", {}))
+    with torch.no_grad():          # un-zero the adaLN / output layers so no kernel sees degenerate all-zero operands
+        g = torch.Generator().manual_seed(1)
+        for p in model.parameters():
+            if p.requires_grad and float(p.abs().max()) == 0.0:
+                p.copy_(torch.randn(p.shape, generator=g) * 0.02)
+    model = model.to(dev).train()
+    loss_fn = SILoss(enc_names=cfg["enc_names"], loss_weights=cfg["loss_weights"])
+    return ReedTrainer(model, loss_fn, precision=precision), spec
+
+
+def make_batches(cfg, spec, dev, n_buf):
+    """n_buf synthetic batches: [(pinned host tensors, device-resident copies)]."""
+    B, S, T = cfg["local_batch"], cfg["input_size"], spec.tokens
+    out = []
+    for _ in range(n_buf):
+        x = torch.randn(B, 4, S, S).pin_memory()
+        y = torch.randint(0, 1000, (B,)).pin_memory()
+        zs = [(torch.randn(B, T, z) if k == "i" else torch.randn(B, z)).bfloat16().pin_memory()
+              for z, k in zip(cfg["z_dims"], cfg["z_types"])]
+        out.append(((x, y, zs), (x.to(dev), y.to(dev), [z.to(dev) for z in zs])))
+    return out
+
+
+def run_gpu_arm(args, cfg):
+    import torch.distributed as dist
+    from reed_b200 import _cabi, ops
     from oracle.sit_oracle import flops_per_image
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -165,33 +196,13 @@ def run_gpu_arm(args, cfg):
     _cabi.load()
     ops.device_check()
 
-    spec = spec_for(cfg)
+    trainer, spec = build_trainer(cfg, dev)
     B, S, T = cfg["local_batch"], cfg["input_size"], spec.tokens
-    torch.manual_seed(0)          # same init on every rank; the trainer also broadcasts rank 0's weights
-    model = SiT_models[cfg["model"]](input_size=S, num_classes=1000, use_cfg=True, z_dims=cfg["z_dims"],
-                                     z_types=cfg["z_types"], encoder_depth=cfg["encoder_depth"],
-                                     encoder_depth_text=cfg["encoder_depth_text"], fused_attn=True, qk_norm=False,
-                                     **cfg.get("extra", {}))
-    with torch.no_grad():          # un-zero the adaLN / output layers so no kernel sees degenerate all-zero operands
-        g = torch.Generator().manual_seed(1)
-        for p in model.parameters():
-            if p.requires_grad and float(p.abs().max()) == 0.0:
-                p.copy_(torch.randn(p.shape, generator=g) * 0.02)
-    model = model.to(dev).train()
-    loss_fn = SILoss(enc_names=cfg["enc_names"], loss_weights=cfg["loss_weights"])
-    trainer = ReedTrainer(model, loss_fn, precision="bf16")
-
-    torch.manual_seed(1234 + rank)     # per-rank data/RNG streams (train.py:176)
     n_buf = 4
-
-    def make_host_batch():
-        x = torch.randn(B, 4, S, S).pin_memory()
-        y = torch.randint(0, 1000, (B,)).pin_memory()
-        zs = [(torch.randn(B, T, z) if k == "i" else torch.randn(B, z)).bfloat16().pin_memory()
-              for z, k in zip(cfg["z_dims"], cfg["z_types"])]
-        return x, y, zs
-    host = [make_host_batch() for _ in range(n_buf)]
-    resident = [(x.to(dev), y.to(dev), [z.to(dev) for z in zs]) for x, y, zs in host]
+    torch.manual_seed(1234 + rank)     # per-rank data/RNG streams (train.py:176)
+    batches = make_batches(cfg, spec, dev, n_buf)
+    host = [h for h, _ in batches]
+    resident = [r for _, r in batches]
     h2d_bytes = sum(t.numel() * t.element_size() for t in (host[0][0], host[0][1], *host[0][2]))
 
     def barrier():
