@@ -13,6 +13,7 @@
  *   - dtype codes: 0 = float32, 1 = bfloat16.  "act dtype" is the activation dtype of the precision mode
  *     (0: fp32 mode, parity bar 1e-5 relative; 1: bf16 tensor-core mode, parity bar 2e-2 relative)
  *   - backend codes (gemm/attention): 0 = auto, 1 = force the fp32-math SIMT kernel, 2 = require the tensor-core kernel
+ *     (gemm only: 3 / 4 = require the tcgen05 kernel with cta_group::1 / cta_group::2 instead of the planner's choice)
  */
 #ifndef REED_B200_H_
 #define REED_B200_H_

@@ -20,6 +20,7 @@ int gemm_simt(int act_dtype, const void* A, int64_t lda, int a_mn, const void* B
 int gemm_tcgen05(const void* A, int64_t lda, int a_mn, const void* B, int64_t ldb, int b_mn, void* D, int64_t ldd,
                  int d_dtype, int M, int N, int K, const EpiParams& ep, cudaStream_t st);
 bool gemm_tcgen05_supported(int64_t lda, int64_t ldb, int64_t ldd, const void* A, const void* B, int M, int N, int K);
+void gemm_tcgen05_force_cta_group(int cg);
 int attn_simt_fwd(int act_dtype, const void* qkv, void* o, float* lse, int B, int T, int H, int hd, cudaStream_t st);
 int attn_simt_bwd(int act_dtype, const void* qkv, const void* o, const void* d_o, const float* lse, void* dqkv,
                   float* delta, int B, int T, int H, int hd, cudaStream_t st);
@@ -47,7 +48,8 @@ extern "C" int reed_device_check(char* name, int name_len) {
   return 0;
 }
 
-// backend: 0 auto (tcgen05 for bf16 activations when the shape allows, else SIMT), 1 force SIMT, 2 require tcgen05
+// backend: 0 auto (tcgen05 for bf16 activations when the shape allows, else SIMT), 1 force SIMT, 2 require tcgen05,
+// 3 / 4 require tcgen05 with cta_group::1 / cta_group::2 (test knob; the planner normally picks)
 extern "C" int reed_gemm(int act_dtype, const void* A, int64_t lda, int a_mn_major, const void* B, int64_t ldb,
                          int b_mn_major, void* D, int64_t ldd, int d_dtype, int M, int N, int K, int epilogue,
                          const void* bias, const void* aux, int64_t ld_aux, const void* gate, int64_t ld_gate,
@@ -66,9 +68,11 @@ extern "C" int reed_gemm(int act_dtype, const void* A, int64_t lda, int a_mn_maj
   cudaStream_t st = (cudaStream_t)stream;
   const bool tc_ok = act_dtype == kBF16 && gemm_tcgen05_supported(lda, ldb, ldd, A, B, M, N, K) &&
                      (ld_aux % 4 == 0) && (ld_out2 % 4 == 0) && (ld_gate % 4 == 0);
-  if (backend == 2) REED_REQUIRE(tc_ok, "gemm: tcgen05 path required but shape/dtype unsupported (M=%d N=%d K=%d)", M, N, K);
-  if (backend != 1 && tc_ok)
+  if (backend >= 2) REED_REQUIRE(tc_ok, "gemm: tcgen05 path required but shape/dtype unsupported (M=%d N=%d K=%d)", M, N, K);
+  if (backend != 1 && tc_ok) {
+    gemm_tcgen05_force_cta_group(backend == 3 ? 1 : (backend == 4 ? 2 : 0));
     return gemm_tcgen05(A, lda, a_mn_major, B, ldb, b_mn_major, D, ldd, d_dtype, M, N, K, ep, st);
+  }
   return gemm_simt(act_dtype, A, lda, a_mn_major, B, ldb, b_mn_major, D, ldd, d_dtype, M, N, K, ep, st);
 }
 

@@ -1,0 +1,642 @@
+// bf16 GEMM on the 5th-generation tensor cores (tcgen05.mma, fp32 accumulators in TMEM), operands staged in
+// shared memory by TMA with the 128-byte swizzle, persistent over output tiles, warp-specialised:
+//   warp 0    : TMA producer          (one elected lane)
+//   warp 1    : tcgen05.mma issuer    (one elected lane), commits free smem stages / publish accumulators
+//   warp 2    : TMEM allocator
+//   warps 4-11: epilogue - tcgen05.ld the 128 x BN accumulator, transpose through smem so global accesses are
+//               row-coalesced, apply the fused epilogue (bias / GELU / SiLU / gate*y+residual / act') and store.
+// Two accumulator stages in TMEM let the epilogue of tile i overlap the MMAs of tile i+1.
+//
+// CG = 2 (`cta_group::2`): a CTA pair on one TPC computes a 256 x BN tile.  Each CTA stages its own 128 rows of A
+// and its own BN/2 rows of B (half the L2->SM operand traffic per FLOP of the single-CTA kernel, which is what
+// bounds these GEMMs on B200), the leader CTA issues the M = 256 MMAs for both, every CTA drains the 128
+// accumulator rows that live in its own TMEM.
+//
+//   D[M,N] = epi( A[M,K] . B[N,K]^T )        A, B bf16; each either K-major or MN-major in global memory:
+//   forward  y  = x W^T      : A = x  (K-major),  B = W  (K-major)
+//   dgrad    dx = dy W       : A = dy (K-major),  B = W  (MN-major: stored [N_contract, K_out])
+//   wgrad    dW = dy^T x     : A = dy (MN-major), B = x  (MN-major)
+// This covers the qkv / proj / fc1 / fc2 / adaLN / projector linears of /root/reference/image/models/sit.py
+// (timm Attention.qkv/proj, Mlp.fc1/fc2 at sit.py:114-124; adaLN 125-128; build_mlp 17-24) and their backward.
+#pragma once
+#include <cuda.h>
+#include <stdlib.h>
+#include "common.cuh"
+
+namespace reed {
+
+constexpr int BM = 128;         // accumulator rows per CTA (UMMA M = 128 x CG)
+constexpr int BK = 64;          // 64 bf16 = 128 B = one swizzle row
+constexpr int UMMA_K = 16;
+constexpr int kGemmThreads = 384;   // warps 0-3: TMA / MMA / TMEM alloc / spare; warps 4-11: epilogue
+constexpr int kEpiWarps = 8;
+constexpr int kStageCols = 32;  // accumulator columns moved per tcgen05.ld
+constexpr int kStagePitch = 36; // floats; 144 B row pitch keeps float4 smem accesses conflict-free
+
+// ------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t done = 0;
+  uint64_t spins = 0;
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (done) break;
+    if (++spins > (1ull << 26)) {   // ~seconds: a protocol bug must surface as an error, never as a hung GPU
+      printf("reed gemm: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+// cta_group::2: the executing CTA's TMA lands in its own smem but reports its bytes to the LEADER CTA's mbarrier
+// (`bar_cluster_addr` = shared::cluster address of that barrier, from mapa)
+__device__ __forceinline__ void tma_load_2d_cg2(const CUtensorMap* map, uint32_t bar_cluster_addr, void* dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+// shared::cluster address of the same smem variable in CTA `rank` of this cluster
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t local_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster_addr) {
+  // relaxed: the barrier orders TMEM reuse (tcgen05.wait::ld + tcgen05.fence precede it), not global memory, so the
+  // arrive need not wait for this warp's outstanding global stores (a release at cluster scope would)
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+// CG = 1: one CTA; CG = 2: a CTA pair (both CTAs' allocator warps execute the cta_group::2 forms)
+template <int CG>
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t cols) {
+  if constexpr (CG == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  } else {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+}
+template <int CG>
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
+  if constexpr (CG == 1)
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+  else
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+template <int CG>
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                          uint32_t accumulate) {
+  if constexpr (CG == 1)
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+  else
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// mbarrier arrives once every previously issued tcgen05.mma of this thread has completed; with CG = 2 the arrive is
+// multicast to the barrier at the same smem offset in both CTAs of the pair
+template <int CG>
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  if constexpr (CG == 1)
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+  else
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"((uint16_t)3)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout), SWIZZLE_128B, version 1.
+//   K-major : rows of 128 B, 8-row swizzle atoms 1024 B apart            -> SBO = 1024, LBO unused
+//   MN-major: each TMA box is 64 (mn) x BK (k) elements: k-rows of 128 B, -> SBO = 1024 (next 8 k-rows),
+//             the next 64 mn-elements live in the next box               -> LBO = BK * 128 B
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;   // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;   // SWIZZLE_128B
+  return d;
+}
+
+// cute::UMMA::InstrDescriptor: D fp32, A/B bf16, dense
+__host__ __device__ constexpr uint32_t make_idesc(int m, int n, int a_mn, int b_mn) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) |
+         ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+// ------------------------------------------------------------------------------------------------
+// fast epilogue math (bf16 tensor-core mode only; the fp32 mode runs the SIMT kernel with precise math)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float tanh_fast(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float gelu_fast(float x) {
+  const float k0 = 0.7978845608028654f, k1 = 0.044715f;
+  return 0.5f * x * (1.f + tanh_fast(k0 * (x + k1 * x * x * x)));
+}
+__device__ __forceinline__ float gelu_grad_fast(float x) {
+  const float k0 = 0.7978845608028654f, k1 = 0.044715f;
+  const float x2 = x * x;
+  const float th = tanh_fast(k0 * (x + k1 * x * x2));
+  return 0.5f * (1.f + th) + 0.5f * x * (1.f - th * th) * (k0 * (1.f + 3.f * k1 * x2));
+}
+__device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
+__device__ __forceinline__ float silu_fast(float x) { return x * sigmoid_fast(x); }
+__device__ __forceinline__ float silu_grad_fast(float x) {
+  const float s = sigmoid_fast(x);
+  return s * (1.f + x * (1.f - s));
+}
+__device__ __forceinline__ float round_bf16(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
+__device__ __forceinline__ void red_add4(float* p, const F4& f) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(f.v[0]), "f"(f.v[1]), "f"(f.v[2]), "f"(f.v[3])
+               : "memory");
+}
+
+constexpr int kEpiAccum = 6;    // internal: kEpiNone with ep.accumulate (D += acc), fp32 D
+constexpr int kEpiAtomic = 7;   // internal: stream-K partial tile, red.add into fp32 D
+
+template <int CG, int BN>
+struct GemmCfg {
+  static constexpr int kBNL = BN / CG;            // B rows (output columns) staged by each CTA
+  static constexpr int kABytes = BM * BK * 2;
+  static constexpr int kBBytes = kBNL * BK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStagingBytes = kEpiWarps * 32 * kStagePitch * 4;
+  static constexpr int kBudget = 227 * 1024 - 1024 /*align slack*/ - kStagingBytes - 256 /*barriers*/;
+  static constexpr int kStages = (kBudget / kStageBytes) > 8 ? 8 : (kBudget / kStageBytes);
+  static constexpr int kSmemBytes = 1024 + kStages * kStageBytes + kStagingBytes + 256;
+  static constexpr int kTmemCols = 2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512);
+};
+
+// Work distribution.  Data-parallel: output tiles round-robin over the persistent CTAs.  Stream-K (fp32 accumulating
+// outputs, i.e. the weight-gradient GEMMs whose tile count does not fill 148 SMs evenly): the (tile, k-block) units
+// are cut into gridDim.x equal contiguous ranges; a CTA reduces each piece of a tile it owns in TMEM and adds it
+// into the zero-initialised (or accumulating) fp32 output with vector red.global.add.
+struct Seg { int tile, kb0, kb1; };
+struct Sched {
+  int sk, num_tiles, num_kb, tile;
+  int64_t u, u_end;
+  int stride;
+  // `worker` = index of this CTA (CG = 1) or CTA pair (CG = 2) among `workers`
+  __device__ Sched(int sk_, int num_tiles_, int num_kb_, int worker, int workers)
+      : sk(sk_), num_tiles(num_tiles_), num_kb(num_kb_), stride(workers) {
+    tile = worker;
+    const int64_t total = (int64_t)num_tiles * num_kb;
+    u = total * worker / workers;
+    u_end = total * (worker + 1) / workers;
+  }
+  __device__ bool next(Seg& s) {
+    if (!sk) {
+      if (tile >= num_tiles) return false;
+      s.tile = tile; s.kb0 = 0; s.kb1 = num_kb;
+      tile += stride;
+      return true;
+    }
+    if (u >= u_end) return false;
+    const int t = (int)(u / num_kb);
+    const int kb0 = (int)(u - (int64_t)t * num_kb);
+    const int64_t left = u_end - u;
+    const int len = (num_kb - kb0) < left ? (num_kb - kb0) : (int)left;
+    s.tile = t; s.kb0 = kb0; s.kb1 = kb0 + len;
+    u += len;
+    return true;
+  }
+};
+
+// One epilogue warp's share of one accumulator tile: TMEM lane quadrant q (32 rows), every second 32-column chunk.
+// Per chunk: tcgen05.ld (thread = row) -> smem transpose -> row-coalesced fused epilogue.  Everything a chunk needs
+// from global memory (residual / saved pre-activation / old D rows, bias and gate vectors) is fetched in ONE batch
+// of independent loads: for the first chunk before the accumulator is even complete (the latency hides behind the
+// MMAs), for chunk i+1 right after the stores of chunk i.  No load is issued between a prefetch batch and its use,
+// so a scoreboard wait never covers a younger load; the other seven epilogue warps fill the remaining latency.
+template <int KIND, int BN, typename TD>
+__device__ __forceinline__ void epilogue_tile(const EpiParams& ep, TD* __restrict__ D, int64_t ldd, int M, int N, int m0,
+                                              int n0, uint32_t taddr, float* __restrict__ st, int q, int half, int lane,
+                                              uint64_t* tfull_bar, uint32_t tfull_phase) {
+  constexpr bool kAuxF32 = KIND == kEpiGateRes || KIND == kEpiAccum;
+  constexpr bool kAuxBf16 = KIND == kEpiDGelu || KIND == kEpiDSilu;
+  constexpr int NCH = BN / kStageCols;
+  const int rsub = lane >> 3, cc = (lane & 7) * 4;
+  const int row_base = m0 + q * 32;
+
+  const float* auxf = nullptr;
+  const bf16* auxh = nullptr;
+  int64_t ld_aux = 0;
+  if constexpr (KIND == kEpiAccum) { auxf = reinterpret_cast<const float*>(D); ld_aux = ldd; }
+  if constexpr (KIND == kEpiGateRes) { auxf = reinterpret_cast<const float*>(ep.aux); ld_aux = ep.ld_aux; }
+  if constexpr (kAuxBf16) { auxh = reinterpret_cast<const bf16*>(ep.aux); ld_aux = ep.ld_aux; }
+
+  float4 af[kAuxF32 ? 8 : 1];
+  uint2 ah[kAuxBf16 ? 8 : 1];
+  float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f), g4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  // gate rows: one per group of rows_per_group rows.  Normally a warp's 32 rows sit in one group (T % 32 == 0) and
+  // the gate vector is fetched once per chunk; otherwise per row.
+  int g_first = 0;
+  bool g_uniform = true;
+  if constexpr (KIND == kEpiGateRes) {
+    g_first = row_base / ep.rows_per_group;
+    const int last = (row_base + 31 < M ? row_base + 31 : M - 1) / ep.rows_per_group;
+    g_uniform = g_first == last || row_base >= M;
+  }
+
+  auto prefetch = [&](int c0) {
+    const int col = n0 + c0 + cc;
+    if (col < N) {
+      if (ep.bias != nullptr) b4 = __ldg(reinterpret_cast<const float4*>(ep.bias + col));
+      if constexpr (KIND == kEpiGateRes) {
+        if (g_uniform) g4 = __ldg(reinterpret_cast<const float4*>(ep.gate + (int64_t)g_first * ep.ld_gate + col));
+      }
+      if constexpr (kAuxF32 || kAuxBf16) {
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const int row = row_base + it * 4 + rsub;
+          if (row < M) {
+            if constexpr (kAuxF32) af[it] = __ldg(reinterpret_cast<const float4*>(auxf + (int64_t)row * ld_aux + col));
+            if constexpr (kAuxBf16) ah[it] = __ldg(reinterpret_cast<const uint2*>(auxh + (int64_t)row * ld_aux + col));
+          }
+        }
+      }
+    }
+  };
+
+  int ci = half;
+  if (ci < NCH && n0 + ci * kStageCols < N) prefetch(ci * kStageCols);
+  mbar_wait(tfull_bar, tfull_phase);
+  tc_fence_after();
+
+#pragma unroll 1
+  for (; ci < NCH; ci += 2) {
+    const int c0 = ci * kStageCols;
+    if (n0 + c0 >= N) break;                 // warp-uniform
+    {
+      float v[32];
+      tmem_ld32(taddr + c0, v);
+      // thread = accumulator row: park the 32 columns in smem ...
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        *reinterpret_cast<float4*>(st + lane * kStagePitch + j * 4) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    }
+    __syncwarp();
+    // ... and pick them up row-coalesced: 8 lanes cover one 32-column row segment, 4 rows per instruction
+    const int col = n0 + c0 + cc;
+    const bool col_ok = col < N;
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int r = it * 4 + rsub;
+      const int row = row_base + r;
+      const float4 f = *reinterpret_cast<const float4*>(st + r * kStagePitch + cc);
+      if (row < M && col_ok) {
+        F4 acc{{f.x + b4.x, f.y + b4.y, f.z + b4.z, f.w + b4.w}};
+        TD* dptr = D + (int64_t)row * ldd + col;
+        if constexpr (KIND == kEpiNone) {
+          store4(dptr, acc);
+        } else if constexpr (KIND == kEpiAccum) {
+          const float4 o = af[it];
+          acc.v[0] += o.x; acc.v[1] += o.y; acc.v[2] += o.z; acc.v[3] += o.w;
+          store4(dptr, acc);
+        } else if constexpr (KIND == kEpiAtomic) {
+          red_add4(reinterpret_cast<float*>(dptr), acc);
+        } else if constexpr (KIND == kEpiGelu || KIND == kEpiSilu) {
+          if (ep.out2) store4(reinterpret_cast<bf16*>(ep.out2) + (int64_t)row * ep.ld_out2 + col, acc);
+          F4 o;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float h = round_bf16(acc.v[i]);   // activate the value backward will see
+            o.v[i] = KIND == kEpiGelu ? gelu_fast(h) : silu_fast(h);
+          }
+          store4(dptr, o);
+        } else if constexpr (KIND == kEpiGateRes) {
+          if (ep.out2) store4(reinterpret_cast<bf16*>(ep.out2) + (int64_t)row * ep.ld_out2 + col, acc);
+          const float4 rs = af[it];
+          float4 g = g4;
+          if (!g_uniform) g = __ldg(reinterpret_cast<const float4*>(ep.gate + (int64_t)(row / ep.rows_per_group) * ep.ld_gate + col));
+          F4 o{{rs.x + g.x * round_bf16(acc.v[0]), rs.y + g.y * round_bf16(acc.v[1]), rs.z + g.z * round_bf16(acc.v[2]),
+                rs.w + g.w * round_bf16(acc.v[3])}};
+          store4(dptr, o);
+        } else {   // kEpiDGelu / kEpiDSilu
+          const uint2 hv = ah[it];
+          const __nv_bfloat162 h01 = *reinterpret_cast<const __nv_bfloat162*>(&hv.x);
+          const __nv_bfloat162 h23 = *reinterpret_cast<const __nv_bfloat162*>(&hv.y);
+          const float h[4] = {__low2float(h01), __high2float(h01), __low2float(h23), __high2float(h23)};
+          F4 o;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) o.v[i] = acc.v[i] * (KIND == kEpiDGelu ? gelu_grad_fast(h[i]) : silu_grad_fast(h[i]));
+          store4(dptr, o);
+        }
+      }
+    }
+    __syncwarp();
+    if (ci + 2 < NCH && n0 + c0 + 2 * kStageCols < N) prefetch(c0 + 2 * kStageCols);
+  }
+}
+
+template <int CG, int BN, int A_MN, int B_MN, typename TD>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                    TD* __restrict__ D, int64_t ldd, int M, int N, int K, EpiParams ep, int stream_k, int dbg) {
+  // dbg (profiling only, results are garbage): 1 = no TMA (MMA does not wait for operands), 2 = no MMA issue,
+  // 4 = no epilogue work (accumulators released immediately)
+  using Cfg = GemmCfg<CG, BN>;
+  constexpr int S = Cfg::kStages;
+  constexpr int BNL = Cfg::kBNL;
+  constexpr int BMT = BM * CG;                 // output-tile rows of the CTA (pair)
+  extern __shared__ uint8_t smem_raw[];
+  // 1024-byte alignment for SWIZZLE_128B, by pointer arithmetic on the __shared__ array so that the compiler keeps
+  // the shared address space (ld.shared / st.shared for the epilogue staging, not generic accesses)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* stage_base = smem;
+  float* staging = reinterpret_cast<float*>(smem + S * Cfg::kStageBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S * Cfg::kStageBytes + Cfg::kStagingBytes);
+  uint64_t* full = bars;              // [S]   TMA bytes landed (CG = 2: the leader's copy counts both CTAs' bytes)
+  uint64_t* empty = bars + S;         // [S]   MMAs reading the stage retired (arrives in every CTA of the pair)
+  uint64_t* tfull = bars + 2 * S;     // [2]   accumulator complete (arrives in every CTA of the pair)
+  uint64_t* tempty = bars + 2 * S + 2;  // [2] accumulator drained by all epilogue warps (of both CTAs; leader's copy)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = CG == 1 ? 0u : cluster_ctarank();
+  const bool leader = rank == 0;
+  const int worker = blockIdx.x / CG, workers = gridDim.x / CG;
+  const int tiles_m = (M + BMT - 1) / BMT, tiles_n = (N + BN - 1) / BN;
+  const int num_tiles = tiles_m * tiles_n;
+  const int num_kb = (K + BK - 1) / BK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_a);
+    tma_prefetch_desc(&map_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < S; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tfull[s], 1);
+      mbar_init(&tempty[s], kEpiWarps * CG);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<CG>(tmem_slot, Cfg::kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  if constexpr (CG == 2) cluster_sync_all();   // the peer's barriers are initialised before anything signals them
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0 && lane == 0) {
+    // ============================== TMA producer (every CTA loads its own A rows / B rows) ==============================
+    int stage = 0;
+    uint32_t phase = 0;
+    Sched sched(stream_k, num_tiles, num_kb, worker, workers);
+    Seg sg;
+    while (!(dbg & 1) && sched.next(sg)) {
+      const int m0 = (sg.tile / tiles_n) * BMT + (int)rank * BM;
+      const int n0 = (sg.tile % tiles_n) * BN + (int)rank * BNL;
+      for (int kb = sg.kb0; kb < sg.kb1; ++kb) {
+        mbar_wait(&empty[stage], phase ^ 1);
+        uint8_t* sa = stage_base + stage * Cfg::kStageBytes;
+        uint8_t* sb = sa + Cfg::kABytes;
+        const int k0 = kb * BK;
+        if constexpr (CG == 1) {
+          mbar_expect_tx(&full[stage], Cfg::kStageBytes);
+          if (A_MN) {
+#pragma unroll
+            for (int c = 0; c < BM / 64; ++c) tma_load_2d(&map_a, &full[stage], sa + c * (BK * 128), m0 + c * 64, k0);
+          } else {
+            tma_load_2d(&map_a, &full[stage], sa, k0, m0);
+          }
+          if (B_MN) {
+#pragma unroll
+            for (int c = 0; c < BNL / 64; ++c) tma_load_2d(&map_b, &full[stage], sb + c * (BK * 128), n0 + c * 64, k0);
+          } else {
+            tma_load_2d(&map_b, &full[stage], sb, k0, n0);
+          }
+        } else {
+          if (leader) mbar_expect_tx(&full[stage], CG * Cfg::kStageBytes);
+          const uint32_t fb = mapa_u32(smem_u32(&full[stage]), 0);
+          if (A_MN) {
+#pragma unroll
+            for (int c = 0; c < BM / 64; ++c) tma_load_2d_cg2(&map_a, fb, sa + c * (BK * 128), m0 + c * 64, k0);
+          } else {
+            tma_load_2d_cg2(&map_a, fb, sa, k0, m0);
+          }
+          if (B_MN) {
+#pragma unroll
+            for (int c = 0; c < BNL / 64; ++c) tma_load_2d_cg2(&map_b, fb, sb + c * (BK * 128), n0 + c * 64, k0);
+          } else {
+            tma_load_2d_cg2(&map_b, fb, sb, k0, n0);
+          }
+        }
+        if (++stage == S) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1 && lane == 0 && leader) {
+    // ============================== MMA issuer (leader CTA only) ==============================
+    constexpr uint32_t idesc = make_idesc(BMT, BN, A_MN, B_MN);
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    Sched sched(stream_k, num_tiles, num_kb, worker, workers);
+    Seg sg;
+    while (sched.next(sg)) {
+      mbar_wait(&tempty[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + acc * BN;
+      for (int kb = sg.kb0; kb < sg.kb1; ++kb) {
+        if (!(dbg & 1)) mbar_wait(&full[stage], phase);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(stage_base + stage * Cfg::kStageBytes);
+        const uint32_t sb = sa + Cfg::kABytes;
+#pragma unroll
+        for (int k = 0; k < BK / UMMA_K; ++k) {
+          // K-major: +32 B inside the swizzled 128 B row per 16-element k step; MN-major: +16 k-rows of 128 B
+          const uint64_t da = A_MN ? make_smem_desc(sa + k * (UMMA_K * 128), BK * 128, 1024)
+                                   : make_smem_desc(sa + k * (UMMA_K * 2), 16, 1024);
+          const uint64_t db = B_MN ? make_smem_desc(sb + k * (UMMA_K * 128), BK * 128, 1024)
+                                   : make_smem_desc(sb + k * (UMMA_K * 2), 16, 1024);
+          if (!(dbg & 2)) umma_bf16<CG>(tmem_d, da, db, idesc, (kb > sg.kb0 || k > 0) ? 1u : 0u);
+        }
+        umma_commit<CG>(&empty[stage]);
+        if (++stage == S) { stage = 0; phase ^= 1; }
+      }
+      umma_commit<CG>(&tfull[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  } else if (warp >= 4) {
+    // ============================== epilogue (8 warps per CTA, this CTA's 128 accumulator rows) ==============================
+    const int q = warp & 3;                      // TMEM lane quadrant this warp may access
+    const int half = (warp - 4) >> 2;            // which 32-column chunks (even / odd) this warp drains
+    float* st = staging + (warp - 4) * 32 * kStagePitch;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    Sched sched(stream_k, num_tiles, num_kb, worker, workers);
+    Seg sg;
+    while (sched.next(sg)) {
+      const int m0 = (sg.tile / tiles_n) * BMT + (int)rank * BM, n0 = (sg.tile % tiles_n) * BN;
+      const uint32_t taddr = tmem_base + acc * BN + ((uint32_t)(q * 32) << 16);
+#define REED_EPI(KIND) epilogue_tile<KIND, BN, TD>(ep, D, ldd, M, N, m0, n0, taddr, st, q, half, lane, &tfull[acc], acc_phase)
+      if (dbg & 4) {
+        mbar_wait(&tfull[acc], acc_phase);
+      } else if constexpr (sizeof(TD) == 4) {
+        if (stream_k) REED_EPI(kEpiAtomic);
+        else if (ep.kind == kEpiGateRes) REED_EPI(kEpiGateRes);
+        else if (ep.kind == kEpiNone && ep.accumulate) REED_EPI(kEpiAccum);
+        else if (ep.kind == kEpiNone) REED_EPI(kEpiNone);
+        else if (ep.kind == kEpiGelu) REED_EPI(kEpiGelu);
+        else if (ep.kind == kEpiSilu) REED_EPI(kEpiSilu);
+        else if (ep.kind == kEpiDGelu) REED_EPI(kEpiDGelu);
+        else REED_EPI(kEpiDSilu);
+      } else {
+        if (ep.kind == kEpiNone) REED_EPI(kEpiNone);
+        else if (ep.kind == kEpiGelu) REED_EPI(kEpiGelu);
+        else if (ep.kind == kEpiSilu) REED_EPI(kEpiSilu);
+        else if (ep.kind == kEpiDGelu) REED_EPI(kEpiDGelu);
+        else REED_EPI(kEpiDSilu);
+      }
+#undef REED_EPI
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if constexpr (CG == 1) mbar_arrive(&tempty[acc]);
+        else mbar_arrive_cluster(mapa_u32(smem_u32(&tempty[acc]), 0));
+      }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+  tc_fence_before();
+  __syncwarp();
+  __syncthreads();
+  if constexpr (CG == 2) cluster_sync_all();   // nobody leaves while the peer may still signal it or read its smem
+  if (warp == 2) tmem_dealloc<CG>(tmem_base, Cfg::kTmemCols);
+}
+
+// ------------------------------------------------------------------------------------------------
+// launch helpers (instantiated in gemm_tcgen05_cg1.cu / gemm_tcgen05_cg2.cu)
+// ------------------------------------------------------------------------------------------------
+template <int CG, int BN, int A_MN, int B_MN, typename TD>
+static int launch(const CUtensorMap& ma, const CUtensorMap& mb, void* D, int64_t ldd, int M, int N, int K,
+                  const EpiParams& ep, cudaStream_t st, int grid, int stream_k) {
+  static const int dbg = getenv("REED_GEMM_DEBUG") ? atoi(getenv("REED_GEMM_DEBUG")) : 0;
+  using Cfg = GemmCfg<CG, BN>;
+  static_assert(Cfg::kStages >= 3, "pipeline too shallow");
+  static_assert(!B_MN || Cfg::kBNL % 64 == 0, "MN-major B is staged in 64-column TMA boxes");
+  auto kernel = gemm_tcgen05_kernel<CG, BN, A_MN, B_MN, TD>;
+  static bool configured = false;   // per template instance
+  if (!configured) {
+    REED_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    configured = true;
+  }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kGemmThreads);
+  cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  REED_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kernel, ma, mb, (TD*)D, ldd, M, N, K, ep, stream_k, dbg));
+  return 0;
+}
+
+template <int CG, int BN, typename TD>
+static int launch_major(int a_mn, int b_mn, const CUtensorMap& ma, const CUtensorMap& mb, void* D, int64_t ldd, int M,
+                        int N, int K, const EpiParams& ep, cudaStream_t st, int grid, int stream_k) {
+  if (!a_mn && !b_mn) return launch<CG, BN, 0, 0, TD>(ma, mb, D, ldd, M, N, K, ep, st, grid, stream_k);
+  if constexpr ((BN / CG) % 64 == 0) {
+    if (!a_mn && b_mn) return launch<CG, BN, 0, 1, TD>(ma, mb, D, ldd, M, N, K, ep, st, grid, stream_k);
+    if (a_mn && b_mn) return launch<CG, BN, 1, 1, TD>(ma, mb, D, ldd, M, N, K, ep, st, grid, stream_k);
+  }
+  if (a_mn && !b_mn) return launch<CG, BN, 1, 0, TD>(ma, mb, D, ldd, M, N, K, ep, st, grid, stream_k);
+  return fail("gemm_tcgen05: no kernel for cta_group::%d BN=%d with MN-major B", CG, BN);
+}
+
+template <int CG>
+static int launch_cg(int bn, int a_mn, int b_mn, const CUtensorMap& ma, const CUtensorMap& mb, void* D, int64_t ldd,
+                     int d_dtype, int M, int N, int K, const EpiParams& ep, cudaStream_t st, int grid, int stream_k) {
+#define GO(BNV)                                                                                                        \
+  (d_dtype == kF32 ? launch_major<CG, BNV, float>(a_mn, b_mn, ma, mb, D, ldd, M, N, K, ep, st, grid, stream_k)         \
+                   : launch_major<CG, BNV, bf16>(a_mn, b_mn, ma, mb, D, ldd, M, N, K, ep, st, grid, stream_k))
+  if (bn == 256) return GO(256);
+  if (bn == 192) return GO(192);
+  return GO(128);
+#undef GO
+}
+
+}  // namespace reed

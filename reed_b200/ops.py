@@ -20,7 +20,7 @@ from ._cabi import call
 F32, BF16 = 0, 1
 EPI_NONE, EPI_GELU, EPI_SILU, EPI_GATE_RES, EPI_DGELU, EPI_DSILU = range(6)
 ACT_NONE, ACT_GELU, ACT_SILU = 0, 1, 2
-BACKEND_AUTO, BACKEND_SIMT, BACKEND_TENSOR = 0, 1, 2
+BACKEND_AUTO, BACKEND_SIMT, BACKEND_TENSOR, BACKEND_TENSOR_CG1, BACKEND_TENSOR_CG2 = 0, 1, 2, 3, 4
 
 _gemm_backend = BACKEND_AUTO
 _attn_backend = BACKEND_AUTO

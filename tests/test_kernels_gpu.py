@@ -53,14 +53,16 @@ def _operands(M, N, K, a_mn, b_mn, dtype):
     return a, b, a_store, b_store
 
 
+@pytest.mark.parametrize("cg", [0, 1, 2])
 @pytest.mark.parametrize("layout", [(0, 0), (0, 1), (1, 1), (1, 0)])
 @pytest.mark.parametrize("shape", GEMM_SHAPES)
-def test_gemm_tcgen05_layouts(ops, shape, layout):
+def test_gemm_tcgen05_layouts(ops, shape, layout, cg):
+    """cg: 0 = the planner's choice, 1 / 2 = force cta_group::1 / the cta_group::2 CTA-pair kernel."""
     M, N, K = shape
     a_mn, b_mn = layout
     if (a_mn and M % 8) or (b_mn and N % 8) or (not a_mn and K % 8) or (not b_mn and K % 8):
         pytest.skip("TMA needs 16-byte row pitches")
-    ops.set_backends(gemm=ops.BACKEND_TENSOR)
+    ops.set_backends(gemm={0: ops.BACKEND_TENSOR, 1: ops.BACKEND_TENSOR_CG1, 2: ops.BACKEND_TENSOR_CG2}[cg])
     a, b, a_s, b_s = _operands(M, N, K, a_mn, b_mn, torch.bfloat16)
     ref = a.float() @ b.float().t()
     out = ops.gemm(a_s, b_s, a_mn=bool(a_mn), b_mn=bool(b_mn), out_dtype=torch.float32)
@@ -70,12 +72,13 @@ def test_gemm_tcgen05_layouts(ops, shape, layout):
     assert _rel(out_bf.float(), ref) < 1e-2
 
 
-@pytest.mark.parametrize("mode", ["fp32_simt", "bf16_simt", "bf16_tensor"])
+@pytest.mark.parametrize("mode", ["fp32_simt", "bf16_simt", "bf16_tensor", "bf16_tensor_cg1", "bf16_tensor_cg2"])
 def test_gemm_epilogues(ops, mode):
     dtype = torch.float32 if mode == "fp32_simt" else torch.bfloat16
-    ops.set_backends(gemm={"fp32_simt": ops.BACKEND_AUTO, "bf16_simt": ops.BACKEND_SIMT, "bf16_tensor": ops.BACKEND_TENSOR}[mode])
+    ops.set_backends(gemm={"fp32_simt": ops.BACKEND_AUTO, "bf16_simt": ops.BACKEND_SIMT, "bf16_tensor": ops.BACKEND_TENSOR,
+                           "bf16_tensor_cg1": ops.BACKEND_TENSOR_CG1, "bf16_tensor_cg2": ops.BACKEND_TENSOR_CG2}[mode])
     tol = 2e-5 if dtype == torch.float32 else 1.5e-2
-    B, T, N, K = 3, 64, 256, 192
+    B, T, N, K = 5, 64, 256, 192        # M = 320: a full and a ragged 128/256-row tile, groups straddling tiles
     M = B * T
     a, w, _, _ = _operands(M, N, K, 0, 0, dtype)
     bias = _rand(N, seed=3)
@@ -110,6 +113,27 @@ def test_gemm_epilogues(ops, mode):
         want = (dy.float() @ w.float()) * grad
         got = ops.gemm(dy, w, b_mn=True, out_dtype=dtype, epilogue=epi, aux=hsave)
         assert _rel(got.float(), want) < tol
+
+
+@pytest.mark.parametrize("cg", [0, 1, 2])
+@pytest.mark.parametrize("shape", [(1152, 1152, 8192), (3456, 1152, 4096), (1152, 4608, 2048), (384, 1536, 8192)])
+def test_gemm_stream_k_wgrad(ops, shape, cg):
+    """Weight-gradient shapes whose tile count does not fill the SMs take the stream-K path (fp32 red.add partials)."""
+    ops.set_backends(gemm={0: ops.BACKEND_TENSOR, 1: ops.BACKEND_TENSOR_CG1, 2: ops.BACKEND_TENSOR_CG2}[cg])
+    M, N, K = shape                                        # dW[M=N_out, N=K_in] = dy^T x, reduction over K tokens
+    dy = _rand(K, M, dtype=torch.bfloat16, seed=11)
+    x = _rand(K, N, dtype=torch.bfloat16, scale=K ** -0.5, seed=12)
+    ref = dy.float().t() @ x.float()
+    out = torch.full((M, N), 7.0, device=DEV)              # stale contents must be overwritten, not accumulated
+    ops.gemm(dy, x, a_mn=True, b_mn=True, out=out)
+    torch.cuda.synchronize()
+    assert _rel(out, ref) < 2e-5, shape
+    ops.gemm(dy, x, a_mn=True, b_mn=True, out=out, accumulate=True)
+    assert _rel(out, 2 * ref) < 2e-5, shape
+    # a strided destination (a view into a flat gradient bucket row-block)
+    big = torch.zeros((M, N + 64), device=DEV)
+    ops.gemm(dy, x, a_mn=True, b_mn=True, out=big[:, :N])
+    assert _rel(big[:, :N], ref) < 2e-5 and float(big[:, N:].abs().max()) == 0.0
 
 
 def test_gemm_simt_skinny_and_split_k(ops):
