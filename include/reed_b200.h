@@ -64,6 +64,14 @@ int reed_ln_modulate_fwd(const void* x, const void* shift, const void* scale, in
 int reed_ln_modulate_bwd(const void* dout, int act_dtype, const void* x, const void* mean, const void* rstd,
                          const void* scale, int64_t ld_mod, int rows_per_group, const void* dres, void* dx,
                          void* dshift, void* dscale, int M, int D, void* stream);
+/* The two above in one pass over the rows: dx as in reed_ln_modulate_bwd, then the gate backward applied to that dx
+ * (dy = gate[g] * dx, dgate[g] += sum dx * y, dbias += column sums of dy).  Used for the MLP-branch LayerNorm backward
+ * followed by the attention-branch gate backward of the same block (models/sit.py:134-135): the fp32 residual gradient
+ * is written once and not re-read.  gate/dgate share ld_mod with scale/dshift/dscale (views of one [B, 6D] buffer). */
+int reed_ln_modulate_gate_bwd(const void* dout, int act_dtype, const void* x, const void* mean, const void* rstd,
+                              const void* scale, int64_t ld_mod, int rows_per_group, const void* dres, void* dx,
+                              void* dshift, void* dscale, const void* y, const void* gate, void* dy, void* dgate,
+                              void* dbias, int M, int D, void* stream);
 /* Backward of x_new = x + gate[g] * y (models/sit.py:134-135): dy = gate * dxn (act dtype), dgate[g] += sum dxn * y,
  * dbias (optional, fp32 [D]) += column sums of dy. */
 int reed_gate_bwd(const void* dxn, const void* y, int act_dtype, const void* gate, int64_t ld_mod, int rows_per_group,

@@ -21,6 +21,7 @@ _SIGNATURES = {
     "reed_attn_bwd": [I, P, P, P, P, P, P, I, I, I, I, I, P],
     "reed_ln_modulate_fwd": [P, P, P, L, I, P, I, P, P, I, I, F, P],
     "reed_ln_modulate_bwd": [P, I, P, P, P, P, L, I, P, P, P, P, I, I, P],
+    "reed_ln_modulate_gate_bwd": [P, I, P, P, P, P, L, I, P, P, P, P, P, P, P, P, P, I, I, P],
     "reed_gate_bwd": [P, P, I, P, L, I, P, P, P, I, I, P],
     "reed_colsum": [P, I, L, P, I, I, P],
     "reed_unary": [P, I, P, I, I, L, P],

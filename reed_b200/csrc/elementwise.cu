@@ -4,6 +4,7 @@
 //
 // Reference semantics: /root/reference/image/models/sit.py:26-27 (modulate), 113/119/146 (LayerNorm, no
 // affine, eps 1e-6), 130-137 (block), 153-158 (final layer).
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace reed {
@@ -67,168 +68,194 @@ __global__ void __launch_bounds__(kRowWarps * 32) ln_modulate_fwd_kernel(
 }
 
 // ---------------------------------------------------------------------------------------------
-// Backward of the above, fused with the residual-gradient add:
-//   dx[m,:] = dres[m,:] + rstd * (dxhat - mean(dxhat) - xhat * mean(dxhat*xhat)),  dxhat = dout*(1+scale)
-//   dshift[g,:] += sum_m dout ; dscale[g,:] += sum_m dout*xhat        (fp32 atomics, one per CTA per column)
-// Each CTA owns `rows_per_cta` consecutive rows of ONE group.
+// Row-wise backward kernels of the adaLN-Zero block, one template:
+//   LN   : dx[m,:] = dres[m,:] + rstd * (e - mean(e) - xhat * mean(e*xhat)),  e = dout*(1+scale[g,:])
+//          dshift[g,:] += sum_m dout ; dscale[g,:] += sum_m dout*xhat
+//   GATE : backward of x_new = x + gate[g,:]*y applied to the gradient just produced (LN) or to `dres` (no LN):
+//          dy = gate*dx (act dtype) ; dgate[g,:] += sum_m dx*y ; dbias[:] += sum_m dy   (y = GEMM + bias)
+// LN+GATE fuses the MLP-branch LayerNorm backward with the attention-branch gate backward of the same block, so the
+// fp32 residual gradient dx1 is written once and never re-read by a separate gate kernel.
+//
+// Layout: a CTA owns `rows_per_cta` consecutive rows of ONE group and all D columns; thread t owns the float4 column
+// groups t, t+NT, ... (V per thread), so every global access is a fully coalesced 16 B (8 B for bf16) per lane and the
+// column partial sums live in registers for the CTA's whole row range.  Per row the only cross-thread step is the
+// (sum e, sum e*xhat) block reduction.  Partials are flushed with vector red.global.add (4 floats per op).
 // ---------------------------------------------------------------------------------------------
-template <typename TA, int MAXV>
-__global__ void __launch_bounds__(kRowWarps * 32) ln_modulate_bwd_kernel(
-    const TA* __restrict__ dout, const float* __restrict__ x, const float* __restrict__ mean_in,
-    const float* __restrict__ rstd_in, const float* __restrict__ scale, int64_t ld_mod, int rows_per_group,
-    const float* __restrict__ dres, float* __restrict__ dx, float* __restrict__ dshift, float* __restrict__ dscale,
-    int M, int D, int rows_per_cta) {
-  extern __shared__ float red[];   // [2][kRowWarps][D]
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int chunks_per_group = (rows_per_group + rows_per_cta - 1) / rows_per_cta;
-  const int g = blockIdx.x / chunks_per_group;
-  const int r0 = g * rows_per_group + (blockIdx.x % chunks_per_group) * rows_per_cta;
-  const int r1 = min(r0 + rows_per_cta, (g + 1) * rows_per_group);
-  const float* sc = scale + (int64_t)g * ld_mod;
+struct RowBwdParams {
+  const void* dout;      // LN: [M,D] act dtype
+  const float* x;        // LN: [M,D]
+  const float* mean;     // LN: [M]
+  const float* rstd;     // LN: [M]
+  const float* scale;    // LN: rows of pitch ld_mod
+  const float* dres;     // LN: optional residual gradient; !LN: the incoming gradient [M,D]
+  float* dx;             // LN: [M,D]
+  float* dshift;         // LN: rows of pitch ld_mod
+  float* dscale;
+  const void* y;         // GATE: [M,D] act dtype
+  const float* gate;     // GATE: rows of pitch ld_mod
+  void* dy;              // GATE: [M,D] act dtype
+  float* dgate;          // GATE: rows of pitch ld_mod
+  float* dbias;          // GATE: optional [D]
+  int64_t ld_mod;
+  int M, D, rows_per_group, rows_per_cta;
+};
 
-  F4 one_plus[MAXV], acc_sh[MAXV], acc_sc[MAXV];
+__device__ __forceinline__ void red_add_v4(float* p, const F4& f) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(f.v[0]), "f"(f.v[1]), "f"(f.v[2]), "f"(f.v[3])
+               : "memory");
+}
+
+constexpr int kRowMaxThreads = 384;
+
+template <typename TA, int V, bool LN, bool GATE>
+struct RowRegs {           // one row's operands for one thread (V float4 column groups)
+  F4 d[LN ? V : 1], xv[LN ? V : 1], gin[V], yv[GATE ? V : 1];
+  float mean, rstd;
+};
+
+template <typename TA, int V, bool LN, bool GATE>
+__device__ __forceinline__ void row_load(RowRegs<TA, V, LN, GATE>& r, const RowBwdParams& p, int row, const int (&col)[V],
+                                         const bool (&ok)[V]) {
+  const int64_t base = (int64_t)row * p.D;
+  const TA* __restrict__ dout = reinterpret_cast<const TA*>(p.dout);
+  const TA* __restrict__ y = reinterpret_cast<const TA*>(p.y);
 #pragma unroll
-  for (int i = 0; i < MAXV; ++i) {
-    int col = (i * 32 + lane) * 4;
-    acc_sh[i] = F4{{0, 0, 0, 0}};
-    acc_sc[i] = F4{{0, 0, 0, 0}};
-    one_plus[i] = F4{{1, 1, 1, 1}};
-    if (col < D) {
-      F4 s = load4(sc + col);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) one_plus[i].v[j] = 1.f + s.v[j];
-    }
-  }
-  for (int row = r0 + warp; row < r1; row += kRowWarps) {
-    const float mean = mean_in[row], rstd = rstd_in[row];
-    const TA* dor = dout + (int64_t)row * D;
-    const float* xr = x + (int64_t)row * D;
-    F4 xh[MAXV], dh[MAXV];
-    float s1 = 0.f, s2 = 0.f;
-#pragma unroll
-    for (int i = 0; i < MAXV; ++i) {
-      int col = (i * 32 + lane) * 4;
-      if (col < D) {
-        F4 d = load4(dor + col);
-        xh[i] = load4(xr + col);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          float h = (xh[i].v[j] - mean) * rstd;
-          xh[i].v[j] = h;
-          acc_sh[i].v[j] += d.v[j];
-          acc_sc[i].v[j] += d.v[j] * h;
-          float e = d.v[j] * one_plus[i].v[j];
-          dh[i].v[j] = e;
-          s1 += e;
-          s2 += e * h;
-        }
+  for (int i = 0; i < V; ++i) {
+    r.gin[i] = F4{{0, 0, 0, 0}};
+    if (ok[i]) {
+      if constexpr (LN) {
+        r.d[i] = load4(dout + base + col[i]);
+        r.xv[i] = load4(p.x + base + col[i]);
       }
-    }
-    const float c1 = warp_sum(s1) / D, c2 = warp_sum(s2) / D;
-    float* dxr = dx + (int64_t)row * D;
-#pragma unroll
-    for (int i = 0; i < MAXV; ++i) {
-      int col = (i * 32 + lane) * 4;
-      if (col < D) {
-        F4 r;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) r.v[j] = rstd * (dh[i].v[j] - c1 - xh[i].v[j] * c2);
-        if (dres != nullptr) {
-          F4 p = load4(dres + (int64_t)row * D + col);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) r.v[j] += p.v[j];
-        }
-        store4(dxr + col, r);
-      }
+      if (!LN || p.dres != nullptr) r.gin[i] = load4(p.dres + base + col[i]);
+      if constexpr (GATE) r.yv[i] = load4(y + base + col[i]);
     }
   }
-  // CTA-level reduce of the column partials, then one atomic per column
-  float* red_sh = red + (int64_t)warp * D;
-  float* red_sc = red + (int64_t)(kRowWarps + warp) * D;
-#pragma unroll
-  for (int i = 0; i < MAXV; ++i) {
-    int col = (i * 32 + lane) * 4;
-    if (col < D) {
-      store4(red_sh + col, acc_sh[i]);
-      store4(red_sc + col, acc_sc[i]);
-    }
-  }
-  __syncthreads();
-  for (int col = threadIdx.x; col < D; col += blockDim.x) {
-    float a = 0.f, b = 0.f;
-#pragma unroll
-    for (int w = 0; w < kRowWarps; ++w) {
-      a += red[(int64_t)w * D + col];
-      b += red[(int64_t)(kRowWarps + w) * D + col];
-    }
-    atomicAdd(dshift + (int64_t)g * ld_mod + col, a);
-    atomicAdd(dscale + (int64_t)g * ld_mod + col, b);
+  if constexpr (LN) {
+    r.mean = p.mean[row];
+    r.rstd = p.rstd[row];
   }
 }
 
-// ---------------------------------------------------------------------------------------------
-// Backward of x_new = x + gate * y:   dy = gate * dxn (act dtype),  dgate[g,:] += sum_m dxn*y,
-// and (optional) dbias[:] += sum_m dy  (y = GEMM + bias, so d bias = column sum of dy).
-// ---------------------------------------------------------------------------------------------
-template <typename TA, int MAXV>
-__global__ void __launch_bounds__(kRowWarps * 32) gate_bwd_kernel(
-    const float* __restrict__ dxn, const TA* __restrict__ y, const float* __restrict__ gate, int64_t ld_mod,
-    int rows_per_group, TA* __restrict__ dy, float* __restrict__ dgate, float* __restrict__ dbias, int M, int D,
-    int rows_per_cta) {
-  extern __shared__ float red[];   // [2][kRowWarps][D]
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int chunks_per_group = (rows_per_group + rows_per_cta - 1) / rows_per_cta;
+template <typename TA, int V, bool LN, bool GATE>
+__global__ void __launch_bounds__(kRowMaxThreads) row_bwd_kernel(const RowBwdParams p) {
+  __shared__ float2 red[2][kRowMaxThreads / 32];
+  const int NT = blockDim.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = NT >> 5;
+  const int D = p.D;
+  const int chunks_per_group = (p.rows_per_group + p.rows_per_cta - 1) / p.rows_per_cta;
   const int g = blockIdx.x / chunks_per_group;
-  const int r0 = g * rows_per_group + (blockIdx.x % chunks_per_group) * rows_per_cta;
-  const int r1 = min(r0 + rows_per_cta, (g + 1) * rows_per_group);
-  const float* gt = gate + (int64_t)g * ld_mod;
-  F4 gv[MAXV], acc_g[MAXV], acc_b[MAXV];
+  const int r0 = g * p.rows_per_group + (blockIdx.x % chunks_per_group) * p.rows_per_cta;
+  const int r1 = min(r0 + p.rows_per_cta, (g + 1) * p.rows_per_group);
+  TA* __restrict__ dy = reinterpret_cast<TA*>(p.dy);
+  const float inv_d = 1.f / D;
+
+  int col[V];
+  bool ok[V];
+  F4 one_plus[LN ? V : 1], gt[GATE ? V : 1];
+  F4 a_sh[LN ? V : 1], a_sc[LN ? V : 1], a_g[GATE ? V : 1], a_b[GATE ? V : 1];
 #pragma unroll
-  for (int i = 0; i < MAXV; ++i) {
-    int col = (i * 32 + lane) * 4;
-    acc_g[i] = F4{{0, 0, 0, 0}};
-    acc_b[i] = F4{{0, 0, 0, 0}};
-    gv[i] = F4{{0, 0, 0, 0}};
-    if (col < D) gv[i] = load4(gt + col);
-  }
-  for (int row = r0 + warp; row < r1; row += kRowWarps) {
+  for (int i = 0; i < V; ++i) {
+    col[i] = (tid + i * NT) * 4;
+    ok[i] = col[i] < D;
+    if constexpr (LN) {
+      a_sh[i] = F4{{0, 0, 0, 0}};
+      a_sc[i] = F4{{0, 0, 0, 0}};
+      one_plus[i] = F4{{1, 1, 1, 1}};
+      if (ok[i]) {
+        const F4 s = load4(p.scale + (int64_t)g * p.ld_mod + col[i]);
 #pragma unroll
-    for (int i = 0; i < MAXV; ++i) {
-      int col = (i * 32 + lane) * 4;
-      if (col < D) {
-        F4 d = load4(dxn + (int64_t)row * D + col);
-        F4 yy = load4(y + (int64_t)row * D + col);
-        F4 o;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          acc_g[i].v[j] += d.v[j] * yy.v[j];
-          o.v[j] = to_f(from_f<TA>(d.v[j] * gv[i].v[j]));
-          acc_b[i].v[j] += o.v[j];
-        }
-        store4(dy + (int64_t)row * D + col, o);
+        for (int j = 0; j < 4; ++j) one_plus[i].v[j] = 1.f + s.v[j];
       }
     }
-  }
-  float* red_g = red + (int64_t)warp * D;
-  float* red_b = red + (int64_t)(kRowWarps + warp) * D;
-#pragma unroll
-  for (int i = 0; i < MAXV; ++i) {
-    int col = (i * 32 + lane) * 4;
-    if (col < D) {
-      store4(red_g + col, acc_g[i]);
-      store4(red_b + col, acc_b[i]);
+    if constexpr (GATE) {
+      a_g[i] = F4{{0, 0, 0, 0}};
+      a_b[i] = F4{{0, 0, 0, 0}};
+      gt[i] = F4{{0, 0, 0, 0}};
+      if (ok[i]) gt[i] = load4(p.gate + (int64_t)g * p.ld_mod + col[i]);
     }
   }
-  __syncthreads();
-  for (int col = threadIdx.x; col < D; col += blockDim.x) {
-    float a = 0.f, b = 0.f;
+
+  // software pipeline over rows: the loads of row r+1 are in flight while row r is reduced and stored
+  RowRegs<TA, V, LN, GATE> cur, nxt;
+  row_load<TA, V, LN, GATE>(cur, p, r0, col, ok);
+  int buf = 0;
+  for (int row = r0; row < r1; ++row) {
+    if (row + 1 < r1) row_load<TA, V, LN, GATE>(nxt, p, row + 1, col, ok);
+    const int64_t base = (int64_t)row * D;
+    if constexpr (LN) {
+      const float mean = cur.mean, rstd = cur.rstd;
+      float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-    for (int w = 0; w < kRowWarps; ++w) {
-      a += red[(int64_t)w * D + col];
-      b += red[(int64_t)(kRowWarps + w) * D + col];
+      for (int i = 0; i < V; ++i) {
+        if (ok[i]) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float h = (cur.xv[i].v[j] - mean) * rstd;
+            const float dv = cur.d[i].v[j];
+            cur.xv[i].v[j] = h;
+            a_sh[i].v[j] += dv;
+            a_sc[i].v[j] += dv * h;
+            const float e = dv * one_plus[i].v[j];
+            cur.d[i].v[j] = e;
+            s1 += e;
+            s2 += e * h;
+          }
+        }
+      }
+      s1 = warp_sum(s1);
+      s2 = warp_sum(s2);
+      if (nwarps > 1) {
+        if (lane == 0) red[buf][warp] = make_float2(s1, s2);
+        __syncthreads();
+        s1 = 0.f;
+        s2 = 0.f;
+        for (int w = 0; w < nwarps; ++w) {
+          const float2 t = red[buf][w];
+          s1 += t.x;
+          s2 += t.y;
+        }
+        buf ^= 1;    // the next row uses the other slot: one barrier per row is enough
+      }
+      const float c1 = s1 * inv_d, c2 = s2 * inv_d;
+#pragma unroll
+      for (int i = 0; i < V; ++i) {
+        if (ok[i]) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) cur.gin[i].v[j] += rstd * (cur.d[i].v[j] - c1 - cur.xv[i].v[j] * c2);
+          store4(p.dx + base + col[i], cur.gin[i]);
+        }
+      }
     }
-    atomicAdd(dgate + (int64_t)g * ld_mod + col, a);
-    if (dbias != nullptr) atomicAdd(dbias + col, b);
+    if constexpr (GATE) {
+#pragma unroll
+      for (int i = 0; i < V; ++i) {
+        if (ok[i]) {
+          F4 o;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            a_g[i].v[j] += cur.gin[i].v[j] * cur.yv[i].v[j];
+            o.v[j] = to_f(from_f<TA>(cur.gin[i].v[j] * gt[i].v[j]));
+            a_b[i].v[j] += o.v[j];
+          }
+          store4(dy + base + col[i], o);
+        }
+      }
+    }
+    cur = nxt;
+  }
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    if (ok[i]) {
+      const int64_t off = (int64_t)g * p.ld_mod + col[i];
+      if constexpr (LN) {
+        red_add_v4(p.dshift + off, a_sh[i]);
+        red_add_v4(p.dscale + off, a_sc[i]);
+      }
+      if constexpr (GATE) {
+        red_add_v4(p.dgate + off, a_g[i]);
+        if (p.dbias != nullptr) red_add_v4(p.dbias + col[i], a_b[i]);
+      }
+    }
   }
 }
 
@@ -361,33 +388,25 @@ static int ln_fwd_dispatch(const float* x, const float* shift, const float* scal
   return 0;
 }
 
-template <typename TA>
-static int ln_bwd_dispatch(const void* dout, const float* x, const float* mean, const float* rstd, const float* scale,
-                           int64_t ld_mod, int rpg, const float* dres, float* dx, float* dshift, float* dscale, int M,
-                           int D, cudaStream_t st) {
-  int rows_per_cta = rpg < 32 ? rpg : 32;
-  int chunks = ceil_div(rpg, rows_per_cta);
-  dim3 grid((M / rpg) * chunks), block(kRowWarps * 32);
-  size_t smem = sizeof(float) * 2 * kRowWarps * D;
-  int nv = ceil_div(D, 128);
-#define LN_BWD(V) ln_modulate_bwd_kernel<TA, V><<<grid, block, smem, st>>>((const TA*)dout, x, mean, rstd, scale, ld_mod, rpg, dres, dx, dshift, dscale, M, D, rows_per_cta)
-  if (nv <= 4) LN_BWD(4); else if (nv <= 8) LN_BWD(8); else if (nv <= 12) LN_BWD(12); else LN_BWD(16);
-#undef LN_BWD
-  REED_LAUNCH_CHECK();
-  return 0;
+static int rows_per_cta_for(int M, int rpg) {
+  static const int forced = getenv("REED_ROWS_PER_CTA") ? atoi(getenv("REED_ROWS_PER_CTA")) : 0;
+  int r = forced > 0 ? forced : 8;
+  // keep at least ~4 CTAs per SM in flight; never straddle a group
+  while (!forced && r > 1 && (int64_t)M / r < 4 * kNumSMs) r >>= 1;
+  return r < rpg ? r : rpg;
 }
 
-template <typename TA>
-static int gate_bwd_dispatch(const float* dxn, const void* y, const float* gate, int64_t ld_mod, int rpg, void* dy,
-                             float* dgate, float* dbias, int M, int D, cudaStream_t st) {
-  int rows_per_cta = rpg < 32 ? rpg : 32;
-  int chunks = ceil_div(rpg, rows_per_cta);
-  dim3 grid((M / rpg) * chunks), block(kRowWarps * 32);
-  size_t smem = sizeof(float) * 2 * kRowWarps * D;
-  int nv = ceil_div(D, 128);
-#define GB(V) gate_bwd_kernel<TA, V><<<grid, block, smem, st>>>(dxn, (const TA*)y, gate, ld_mod, rpg, (TA*)dy, dgate, dbias, M, D, rows_per_cta)
-  if (nv <= 4) GB(4); else if (nv <= 8) GB(8); else if (nv <= 12) GB(12); else GB(16);
-#undef GB
+template <typename TA, bool LN, bool GATE>
+static int row_bwd_dispatch(RowBwdParams p, cudaStream_t st) {
+  const int D = p.D;
+  const int V = ceil_div(D, 4 * kRowMaxThreads);            // float4 column groups per thread (1 up to D = 1536)
+  const int threads = ceil_div(ceil_div(D / 4, V), 32) * 32;
+  p.rows_per_cta = rows_per_cta_for(p.M, p.rows_per_group);
+  const int chunks = ceil_div(p.rows_per_group, p.rows_per_cta);
+  dim3 grid((p.M / p.rows_per_group) * chunks), block(threads);
+#define RB(VV) row_bwd_kernel<TA, VV, LN, GATE><<<grid, block, 0, st>>>(p)
+  if (V == 1) RB(1); else RB(2);
+#undef RB
   REED_LAUNCH_CHECK();
   return 0;
 }
@@ -413,33 +432,52 @@ extern "C" int reed_ln_modulate_fwd(const void* x, const void* shift, const void
                                 (float*)mean, (float*)rstd, M, D, eps, st);
 }
 
+#define ROW_MOD_OK(ld) REED_REQUIRE((ld) % 4 == 0, "row kernels need modulation rows with a pitch that is a multiple of 4 floats")
+
 extern "C" int reed_ln_modulate_bwd(const void* dout, int act_dtype, const void* x, const void* mean, const void* rstd,
                                     const void* scale, int64_t ld_mod, int rows_per_group, const void* dres, void* dx,
                                     void* dshift, void* dscale, int M, int D, void* stream) {
   ROW_ARGS_OK(M, D, rows_per_group);
-  REED_REQUIRE(D <= 1536, "ln_modulate_bwd: D <= 1536 (48 KB reduction buffer), got %d", D);
+  ROW_MOD_OK(ld_mod);
   if (M == 0) return 0;
+  RowBwdParams p{};
+  p.dout = dout; p.x = (const float*)x; p.mean = (const float*)mean; p.rstd = (const float*)rstd;
+  p.scale = (const float*)scale; p.dres = (const float*)dres; p.dx = (float*)dx; p.dshift = (float*)dshift;
+  p.dscale = (float*)dscale; p.ld_mod = ld_mod; p.M = M; p.D = D; p.rows_per_group = rows_per_group;
   cudaStream_t st = (cudaStream_t)stream;
-  if (act_dtype == kBF16)
-    return ln_bwd_dispatch<bf16>(dout, (const float*)x, (const float*)mean, (const float*)rstd, (const float*)scale,
-                                 ld_mod, rows_per_group, (const float*)dres, (float*)dx, (float*)dshift, (float*)dscale,
-                                 M, D, st);
-  return ln_bwd_dispatch<float>(dout, (const float*)x, (const float*)mean, (const float*)rstd, (const float*)scale,
-                                ld_mod, rows_per_group, (const float*)dres, (float*)dx, (float*)dshift, (float*)dscale, M,
-                                D, st);
+  if (act_dtype == kBF16) return row_bwd_dispatch<bf16, true, false>(p, st);
+  return row_bwd_dispatch<float, true, false>(p, st);
+}
+
+extern "C" int reed_ln_modulate_gate_bwd(const void* dout, int act_dtype, const void* x, const void* mean,
+                                         const void* rstd, const void* scale, int64_t ld_mod, int rows_per_group,
+                                         const void* dres, void* dx, void* dshift, void* dscale, const void* y,
+                                         const void* gate, void* dy, void* dgate, void* dbias, int M, int D,
+                                         void* stream) {
+  ROW_ARGS_OK(M, D, rows_per_group);
+  ROW_MOD_OK(ld_mod);
+  if (M == 0) return 0;
+  RowBwdParams p{};
+  p.dout = dout; p.x = (const float*)x; p.mean = (const float*)mean; p.rstd = (const float*)rstd;
+  p.scale = (const float*)scale; p.dres = (const float*)dres; p.dx = (float*)dx; p.dshift = (float*)dshift;
+  p.dscale = (float*)dscale; p.y = y; p.gate = (const float*)gate; p.dy = dy; p.dgate = (float*)dgate;
+  p.dbias = (float*)dbias; p.ld_mod = ld_mod; p.M = M; p.D = D; p.rows_per_group = rows_per_group;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (act_dtype == kBF16) return row_bwd_dispatch<bf16, true, true>(p, st);
+  return row_bwd_dispatch<float, true, true>(p, st);
 }
 
 extern "C" int reed_gate_bwd(const void* dxn, const void* y, int act_dtype, const void* gate, int64_t ld_mod,
                              int rows_per_group, void* dy, void* dgate, void* dbias, int M, int D, void* stream) {
   ROW_ARGS_OK(M, D, rows_per_group);
-  REED_REQUIRE(D <= 1536, "gate_bwd: D <= 1536 (48 KB reduction buffer), got %d", D);
+  ROW_MOD_OK(ld_mod);
   if (M == 0) return 0;
+  RowBwdParams p{};
+  p.dres = (const float*)dxn; p.y = y; p.gate = (const float*)gate; p.dy = dy; p.dgate = (float*)dgate;
+  p.dbias = (float*)dbias; p.ld_mod = ld_mod; p.M = M; p.D = D; p.rows_per_group = rows_per_group;
   cudaStream_t st = (cudaStream_t)stream;
-  if (act_dtype == kBF16)
-    return gate_bwd_dispatch<bf16>((const float*)dxn, y, (const float*)gate, ld_mod, rows_per_group, dy, (float*)dgate,
-                                   (float*)dbias, M, D, st);
-  return gate_bwd_dispatch<float>((const float*)dxn, y, (const float*)gate, ld_mod, rows_per_group, dy, (float*)dgate,
-                                  (float*)dbias, M, D, st);
+  if (act_dtype == kBF16) return row_bwd_dispatch<bf16, false, true>(p, st);
+  return row_bwd_dispatch<float, false, true>(p, st);
 }
 
 extern "C" int reed_colsum(const void* src, int act_dtype, int64_t ld, void* out, int M, int N, void* stream) {

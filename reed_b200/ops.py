@@ -162,6 +162,19 @@ def ln_modulate_bwd(dout, x, mean, rstd, scale, rows_per_group, dres, dshift, ds
     return dx
 
 
+def ln_modulate_gate_bwd(dout, x, mean, rstd, scale, rows_per_group, dres, dshift, dscale, y, gate, dgate, dbias):
+    """ln_modulate_bwd followed by gate_bwd on its result, in one pass.  Returns (dx fp32, dy act dtype)."""
+    M, D = x.shape
+    dx = torch.empty_like(x)
+    dy = torch.empty_like(y)
+    ld = scale.stride(0)
+    assert dshift.stride(0) == ld == dscale.stride(0) == gate.stride(0) == dgate.stride(0)
+    _launch("reed_ln_modulate_gate_bwd", _p(dout), _code(dout.dtype), _p(x), _p(mean), _p(rstd), _p(scale), ld,
+            rows_per_group, _p(dres), _p(dx), _p(dshift), _p(dscale), _p(y), _p(gate), _p(dy), _p(dgate), _p(dbias), M, D,
+            _stream())
+    return dx, dy
+
+
 def gate_bwd(dxn, y, gate, rows_per_group, dgate, dbias):
     M, D = dxn.shape
     dy = torch.empty_like(y)
@@ -331,7 +344,7 @@ class LNModulateFn(torch.autograd.Function):
 
 
 class SiTBlockFn(torch.autograd.Function):
-    """One adaLN-Zero transformer block (sit.py:125-137 + timm Attention/Mlp): 8 kernels forward, 21 backward.
+    """One adaLN-Zero transformer block (sit.py:125-137 + timm Attention/Mlp): 8 kernels forward, 20 backward.
 
     x: [B,T,D] fp32 residual stream; c_act: [B,D] = silu(c) in the act dtype (shared by all blocks).
     mod = c_act W_ada^T + b_ada = (shift_a, scale_a, gate_a, shift_m, scale_m, gate_m), fp32 [B,6D].
@@ -402,11 +415,9 @@ class SiTBlockFn(torch.autograd.Function):
         db1 = _bias_grad(b_fc1, dh)
         dw1 = _weight_grad(w_fc1, dh, xm2)
         dxm2 = gemm(dh, W(w_fc1), b_mn=True, out_dtype=act_dtype)
-        dx1 = ln_modulate_bwd(dxm2, x1, mean2, rstd2, sc_m, T, dx2, dsh_m, dsc_m)
-
-        # ---- attention branch:  x1 = x0 + g_a * (attn(xm1) Wp^T + bp)
+        # ---- attention branch:  x1 = x0 + g_a * (attn(xm1) Wp^T + bp); its gate backward rides on the LN backward
         dbp_buf, dbp = bias_buffer(b_proj)
-        dy1 = gate_bwd(dx1, y1, g_a, T, dg_a, dbp_buf)
+        dx1, dy1 = ln_modulate_gate_bwd(dxm2, x1, mean2, rstd2, sc_m, T, dx2, dsh_m, dsc_m, y1, g_a, dg_a, dbp_buf)
         dwp = _weight_grad(w_proj, dy1, o)
         d_o = gemm(dy1, W(w_proj), b_mn=True, out_dtype=act_dtype)
         dqkv = attention_bwd(qkv, o, d_o, lse, B, T, H, hd)

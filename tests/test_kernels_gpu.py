@@ -203,6 +203,35 @@ def test_gate_bwd_and_colsum(ops, dtype):
     assert _rel(out, y.float().sum(0)) < 2e-5
 
 
+@pytest.mark.parametrize("D", [128, 384, 1024, 1152])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_ln_modulate_gate_bwd_fused(ops, D, dtype):
+    """The fused LN-backward + gate-backward equals the two separate kernels' results."""
+    B, T = 3, 40
+    x = _rand(B * T, D, seed=1) * 2 + 0.3
+    mod = _rand(B, 6 * D, scale=0.3, seed=2)
+    scale, gate = mod[:, D:2 * D], mod[:, 2 * D:3 * D]
+    _, mean, rstd = ops.ln_modulate_fwd(x, mod[:, :D], scale, T, dtype)
+    dout = _rand(B * T, D, dtype=dtype, seed=3)
+    dres = _rand(B * T, D, seed=4)
+    y = _rand(B * T, D, dtype=dtype, seed=5)
+    dmod_a, dmod_b = torch.zeros_like(mod), torch.zeros_like(mod)
+    db_a, db_b = torch.zeros(D, device=DEV), torch.zeros(D, device=DEV)
+    dx_ref = ops.ln_modulate_bwd(dout, x, mean, rstd, scale, T, dres, dmod_a[:, :D], dmod_a[:, D:2 * D])
+    dy_ref = ops.gate_bwd(dx_ref, y, gate, T, dmod_a[:, 2 * D:3 * D], db_a)
+    dx, dy = ops.ln_modulate_gate_bwd(dout, x, mean, rstd, scale, T, dres, dmod_b[:, :D], dmod_b[:, D:2 * D], y, gate,
+                                      dmod_b[:, 2 * D:3 * D], db_b)
+    torch.cuda.synchronize()
+    assert _rel(dx, dx_ref) < 1e-6
+    assert _rel(dy.float(), dy_ref.float()) < 1e-6
+    assert _rel(dmod_b, dmod_a) < 2e-5 and _rel(db_b, db_a) < 2e-5
+    # against autograd: d/dx of LN-modulate, then the gate branch
+    xr = x.clone().requires_grad_(True)
+    ref = F.layer_norm(xr, (D,), eps=1e-6).view(B, T, D) * (1 + scale[:, None])
+    ref.backward(dout.float().view(B, T, D))
+    assert _rel(dx, xr.grad + dres) < 2e-5
+
+
 def test_unary_actbwd_tokenmean(ops):
     x = _rand(6, 512, seed=1)
     assert _rel(ops.cast(x, torch.bfloat16).float(), x.bfloat16().float()) == 0.0
