@@ -224,9 +224,19 @@ def run_gpu_arm(args, cfg):
         return float(ms)
 
     # ---- device-resident steps --------------------------------------------------------------------------------
+    # The whole step (SILoss forward, backward with the per-block all-reduces, clip, AdamW, EMA) is captured once as a
+    # CUDA graph and replayed; --eager launches the same kernels one by one from Python instead.
+    graphed = not args.eager
+    launches_per_step = None
+    if graphed:
+        l0 = ops.launch_count
+        trainer.capture(*resident[0], warmup=2)
+        launches_per_step = (ops.launch_count - l0) // 3     # 2 warm-up steps + the recorded one
+    step_fn = trainer.train_step_graphed if graphed else trainer.train_step
+
     def resident_step(i):
         x, y, zs = resident[i % n_buf]
-        trainer.train_step(x, y, zs)
+        step_fn(x, y, zs)
 
     for i in range(max(3, args.warmup)):
         resident_step(i)
@@ -234,7 +244,7 @@ def run_gpu_arm(args, cfg):
     sampler.start()
     launches0 = ops.launch_count
     ms = timed(resident_step, args.steps)
-    launches = ops.launch_count - launches0
+    launches = launches_per_step * args.steps if graphed else ops.launch_count - launches0
     sampler.stop_flag = True
     sampler.join(timeout=2)
     value = world * B * args.steps / (ms / 1e3)
@@ -258,7 +268,7 @@ def run_gpu_arm(args, cfg):
         stage(i + 1)                                     # prefetch the next batch while this one computes
         x, y, zs, ev = staged.pop(i)
         torch.cuda.current_stream().wait_event(ev)
-        loss, _ = trainer.train_step(x, y, zs)
+        loss, _ = step_fn(x, y, zs)
         losses.append(float(loss))                       # D2H read of the step's loss (host sync, like train.py:456-466)
 
     for i in range(2):
@@ -283,13 +293,17 @@ def run_gpu_arm(args, cfg):
             tensor_path = a.dtype == torch.bfloat16 and K >= 64 and N >= 64 and a.stride(0) % 8 == 0 and b.stride(0) % 8 == 0
             records.append((2.0 * M * N * K, s, e, tensor_path))
             return out
+    def eager_step(i):
+        x, y, zs = resident[i % n_buf]
+        trainer.train_step(x, y, zs)
+
     if world > 1:
         dist.barrier()
     if rank == 0:
         ops.gemm = probed
         try:
             for i in range(2):
-                resident_step(i)
+                eager_step(i)
             torch.cuda.synchronize()
         finally:
             ops.gemm = real_gemm
@@ -310,7 +324,7 @@ def run_gpu_arm(args, cfg):
     else:
         # other ranks run the same two extra steps so collectives stay matched
         for i in range(2):
-            resident_step(i)
+            eager_step(i)
         torch.cuda.synchronize()
 
     if rank == 0:
@@ -328,7 +342,8 @@ def run_gpu_arm(args, cfg):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": cfg["workload"], "model": cfg["model"], "local_batch": B, "global_batch": B * world,
                        "tokens": T, "parallelism": f"dp{world}", "l2": "per-step working set (activations, weights) far exceeds the 126 MB L2; "
-                       f"{n_buf} rotating input batches", "precision": "bf16 GEMM operands, fp32 accumulate/residual/master weights"},
+                       f"{n_buf} rotating input batches", "precision": "bf16 GEMM operands, fp32 accumulate/residual/master weights",
+                       "launch": "CUDA graph replay of the whole step" if graphed else "eager (one launch per kernel from Python)"},
             "model_flops_per_image": train_flops,
             "tensor_peak_frac_of_measured_burst": value / world * train_flops / 1e12 / peaks_burst,
             "tensor_peak_frac_of_nominal_2250": value / world * train_flops / 1e12 / 2250.0,
@@ -356,6 +371,7 @@ def main():
     ap.add_argument("--config", default="xl2", choices=sorted(CONFIGS))
     ap.add_argument("--impl", default="reed", choices=["reed", "reference"])
     ap.add_argument("--skip-cpu", action="store_true", help="omit the cpu_baseline leg")
+    ap.add_argument("--eager", action="store_true", help="launch kernels from Python instead of replaying the CUDA graph")
     args = ap.parse_args()
     cfg = CONFIGS[args.config]
     if args.impl == "reference":

@@ -118,11 +118,13 @@ int reed_sampler_cast(const void* x, void* x_model, int model_dtype, int64_t n, 
 /* Optimizer tail over flat fp32 buffers (train.py:94-105 update_ema, 253-259 AdamW, 402-412 clip/step/EMA).
  * grad_sumsq: *out (double) += sum g^2.   adamw_ema: g *= grad_scale * min(1, max_norm/(grad_scale*sqrt(*norm_sq)+1e-6))
  * (norm_sq NULL = no clipping), torch.optim.AdamW update with 1-based `step`, ema = decay*ema + (1-decay)*p, and
- * (optional) bf16 shadow of the new weights for the GEMMs.  ema_update: EMA only (frozen pos_embed). */
+ * (optional) bf16 shadow of the new weights for the GEMMs.  step_dev (optional): device int32 holding the step, read
+ * instead of `step` so that a captured CUDA graph of the train step can be replayed.  ema_update: EMA only (frozen
+ * pos_embed). */
 int reed_grad_sumsq(const void* g, int64_t n, void* out, void* stream);
 int reed_adamw_ema(void* p, const void* g, void* m, void* v, void* ema, void* shadow_bf16, int64_t n,
                    const void* norm_sq, float max_norm, float grad_scale, float lr, float beta1, float beta2, float eps,
-                   float weight_decay, int step, float ema_decay, void* stream);
+                   float weight_decay, int step, float ema_decay, const void* step_dev, void* stream);
 int reed_ema_update(const void* p, void* ema, int64_t n, float decay, void* stream);
 
 #ifdef __cplusplus

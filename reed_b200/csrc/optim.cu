@@ -32,6 +32,7 @@ struct AdamArgs {
   float* p; const float* g; float* m; float* v; float* ema; bf16* shadow;
   int64_t n;
   const double* norm_sq;   // device scalar: sum of squares of ALL gradients (after all-reduce), or null = no clipping
+  const int* step_dev;     // device scalar holding the 1-based step (CUDA-graph replays read it), or null = host `step`
   float max_norm, lr, beta1, beta2, eps, weight_decay, bias_c1, bias_c2_sqrt, ema_decay, grad_scale;
 };
 
@@ -47,6 +48,11 @@ __device__ __forceinline__ void adam_one(const AdamArgs& a, float coef, float& p
 }
 
 __global__ void __launch_bounds__(256) adamw_ema_kernel(AdamArgs a) {
+  if (a.step_dev != nullptr) {     // same double-precision bias corrections the host computes for the scalar-step call
+    const double st = (double)*a.step_dev;
+    a.bias_c1 = (float)(1.0 - pow((double)a.beta1, st));
+    a.bias_c2_sqrt = (float)sqrt(1.0 - pow((double)a.beta2, st));
+  }
   float coef = a.grad_scale;
   if (a.norm_sq != nullptr) {
     float norm = (float)sqrt(*a.norm_sq) * a.grad_scale;
@@ -100,9 +106,10 @@ extern "C" int reed_grad_sumsq(const void* g, int64_t n, void* out, void* stream
 
 extern "C" int reed_adamw_ema(void* p, const void* g, void* m, void* v, void* ema, void* shadow_bf16, int64_t n,
                               const void* norm_sq, float max_norm, float grad_scale, float lr, float beta1, float beta2,
-                              float eps, float weight_decay, int step, float ema_decay, void* stream) {
+                              float eps, float weight_decay, int step, float ema_decay, const void* step_dev,
+                              void* stream) {
   if (n == 0) return 0;
-  REED_REQUIRE(step >= 1, "adamw: step is 1-based");
+  REED_REQUIRE(step >= 1 || step_dev != nullptr, "adamw: step is 1-based");
   REED_REQUIRE((((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v | (uintptr_t)ema) & 15) == 0 &&
                    ((uintptr_t)shadow_bf16 & 7) == 0,
                "adamw: buffers must be 16-byte aligned");
@@ -112,7 +119,7 @@ extern "C" int reed_adamw_ema(void* p, const void* g, void* m, void* v, void* em
   a.max_norm = max_norm; a.lr = lr; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps; a.weight_decay = weight_decay;
   a.bias_c1 = (float)(1.0 - pow((double)beta1, (double)step));
   a.bias_c2_sqrt = (float)sqrt(1.0 - pow((double)beta2, (double)step));
-  a.ema_decay = ema_decay; a.grad_scale = grad_scale;
+  a.ema_decay = ema_decay; a.grad_scale = grad_scale; a.step_dev = (const int*)step_dev;
   adamw_ema_kernel<<<opt_grid(n / 4), 256, 0, (cudaStream_t)stream>>>(a);
   REED_LAUNCH_CHECK();
   return 0;

@@ -116,7 +116,12 @@ class SILoss:
             raise NotImplementedError()
         path = _PATH_CODE[self.path_type]
 
-        time_input = self._sample_time(images.shape[0]).to(device=images.device, dtype=images.dtype)
+        # `time_input=` (a (B,1,1,1) tensor) replaces the CPU-generator draw: the reference swallows unknown **kwargs,
+        # so this is an extension, used by ReedTrainer to keep host RNG out of a captured CUDA graph
+        time_input = kwargs.get("time_input")
+        if time_input is None:
+            time_input = self._sample_time(images.shape[0])
+        time_input = time_input.to(device=images.device, dtype=images.dtype)
         noises = torch.randn_like(images)
         t32 = time_input.flatten().float().contiguous()
         x32 = images.float().contiguous()

@@ -67,10 +67,16 @@ class TimestepEmbedder(nn.Module):
                                  nn.Linear(hidden_size, hidden_size, bias=True))
         self.frequency_embedding_size = frequency_embedding_size
 
+    _freq_cache = {}
+
     @staticmethod
     def positional_embedding(t, dim, max_period=10000):
         half = dim // 2
-        freqs = torch.exp(torch.arange(half, dtype=torch.float32) * (-math.log(max_period) / half)).to(t.device)
+        key = (half, max_period, t.device)
+        freqs = TimestepEmbedder._freq_cache.get(key)
+        if freqs is None:      # CPU exp like the reference (sit.py:57-59), moved once: no H2D copy inside a captured graph
+            freqs = torch.exp(torch.arange(half, dtype=torch.float32) * (-math.log(max_period) / half)).to(t.device)
+            TimestepEmbedder._freq_cache[key] = freqs
         ang = t.float().unsqueeze(1) * freqs.unsqueeze(0)
         emb = torch.cat((ang.cos(), ang.sin()), dim=1)
         if dim % 2:

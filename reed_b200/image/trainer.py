@@ -191,19 +191,26 @@ class ReedTrainer:
         self.step_count = 0
         dev = next(model.parameters()).device
         self._norm_sq = torch.zeros(1, device=dev, dtype=torch.float64)
+        self._step_dev = torch.zeros(1, device=dev, dtype=torch.int32)   # device copy of step_count (graph replays)
+        self._graph = None
         # all-reduce each block's bucket as soon as that block's backward has produced its last gradient
         for i, blk in enumerate(model.blocks):
             bucket = self.state.bucket_of_block(i)
             blk._reed_after_backward = (lambda b=bucket: self.reducer.launch(b))
 
-    def compute_loss(self, images, labels, zs, diffusion_decay=1.0, repa_decay=1.0):
-        out = self.loss_fn(self.model, images, dict(y=labels), zs=zs)
+    def compute_loss(self, images, labels, zs, diffusion_decay=1.0, repa_decay=1.0, time_input=None):
+        """diffusion_decay / repa_decay: Python floats or 0-d device tensors (the curriculum scalars of train.py:363-385)."""
+        extra = {} if time_input is None else {"time_input": time_input}
+        out = self.loss_fn(self.model, images, dict(y=labels), zs=zs, **extra)
         loss = out["denoising_loss"].mean() * diffusion_decay + out["proj_loss"] * (self.proj_coeff * repa_decay)
         return loss, out
 
-    def optimizer_step(self):
+    def optimizer_step(self, device_step=False):
+        """device_step: read the step from the device counter (incremented here by a kernel) instead of passing the
+        host integer - the form a CUDA graph can replay."""
         self.step_count += 1
-        st = torch.cuda.current_stream().cuda_stream
+        self._step_dev += 1
+        st = ops._stream()
         self._norm_sq.zero_()
         for b in self.state.buckets:
             ops._launch("reed_grad_sumsq", b.grad.data_ptr(), b.numel, self._norm_sq.data_ptr(), st)
@@ -214,7 +221,8 @@ class ReedTrainer:
                         b.shadow.data_ptr() if b.shadow is not None else None, b.numel,
                         self._norm_sq.data_ptr() if clip else None, float(self.max_grad_norm or 0.0),
                         self.reducer.grad_scale, self.lr, self.betas[0], self.betas[1], self.eps, self.weight_decay,
-                        self.step_count, self.ema_decay if b.ema is not None else 0.0, st)
+                        0 if device_step else self.step_count, self.ema_decay if b.ema is not None else 0.0,
+                        self._step_dev.data_ptr() if device_step else None, st)
         for p, ep in self.state.frozen:
             if ep is not None:
                 ops._launch("reed_ema_update", p.data_ptr(), ep.data_ptr(), p.numel(), self.ema_decay, st)
@@ -231,3 +239,63 @@ class ReedTrainer:
         self.reducer.finish()
         self.optimizer_step()
         return loss.detach(), out
+
+    # -- CUDA-graph replay of the whole step -----------------------------------------------------------------------
+    # The step launches ~1100 kernels; enqueueing them from Python costs about as long as they run on a B200.  The
+    # graph holds loss forward, backward (with the per-block all-reduces), clip, AdamW, EMA and the shadow refresh.
+    # Host randomness stays outside: the SILoss time draw (CPU generator, loss.py:159) is made here with the same
+    # call and copied into the graph's static input; device randomness (noise, label dropout) is captured through
+    # torch's graph-safe generator state.
+    def _step_body(self, g):
+        self.state.begin_step()
+        loss, out = self.compute_loss(g["images"], g["labels"], g["zs"], g["scalars"][0], g["scalars"][1],
+                                      time_input=g["time"])
+        loss.backward()
+        self.state.finish_backward()
+        self.reducer.finish()
+        self.optimizer_step(device_step=True)
+        return loss.detach(), out
+
+    def capture(self, images, labels, zs, warmup=2):
+        """Record one train step on batches shaped like (images, labels, zs).  The warm-up steps are real optimizer
+        steps on the given batch (they size the allocator pools and run every first-use initialisation)."""
+        dev = images.device
+        g = {"images": images.clone(), "labels": labels.clone(), "zs": [z.clone() for z in zs],
+             "time": torch.zeros((images.shape[0], 1, 1, 1), device=dev, dtype=torch.float32),
+             "scalars": torch.ones(2, device=dev, dtype=torch.float32),
+             "host": torch.zeros(images.shape[0] + 2, dtype=torch.float32).pin_memory()}
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                g["time"].copy_(self.loss_fn._sample_time(images.shape[0]))
+                self._step_body(g)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        steps_before = self.step_count
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            g["loss"], g["out"] = self._step_body(g)
+        self.step_count = steps_before          # capture records, it does not run: undo the host-side counter bump
+        self._step_dev.fill_(steps_before)
+        self._graph, self._g = graph, g
+        return self
+
+    def train_step_graphed(self, images, labels, zs, diffusion_decay=1.0, repa_decay=1.0):
+        """Replay the captured step on a new batch.  Returns (loss, out) as views of the graph's static outputs."""
+        assert self._graph is not None, "call capture() first"
+        g = self._g
+        host = g["host"]
+        bsz = images.shape[0]
+        host[:bsz] = self.loss_fn._sample_time(bsz).flatten()       # the draw SILoss would make (CPU generator)
+        host[bsz] = diffusion_decay
+        host[bsz + 1] = repa_decay
+        g["time"].view(-1).copy_(host[:bsz], non_blocking=True)
+        g["scalars"].copy_(host[bsz:], non_blocking=True)
+        g["images"].copy_(images, non_blocking=True)
+        g["labels"].copy_(labels, non_blocking=True)
+        for dst, src in zip(g["zs"], zs):
+            dst.copy_(src, non_blocking=True)
+        self._graph.replay()
+        self.step_count += 1
+        return g["loss"], g["out"]

@@ -42,7 +42,8 @@ def _code(dtype: torch.dtype) -> int:
 
 
 def _stream() -> int:
-    return torch.cuda.current_stream().cuda_stream
+    """Raw cudaStream_t of torch's current stream on the current device (the stream being captured, under graph capture)."""
+    return torch._C._cuda_getCurrentRawStream(torch.cuda.current_device())
 
 
 def _p(t: Optional[torch.Tensor]):

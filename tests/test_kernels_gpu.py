@@ -42,6 +42,10 @@ GEMM_SHAPES = [
     (77, 72 * 8, 200),     # ragged everything (N % 8 == 0)
     (32, 6912, 1152),      # adaLN: M = batch
     (4096, 768, 64),       # one k-block
+    (6912, 1152, 32),      # adaLN wgrad: reduction over the batch (half a k-block, TMA zero-fill)
+    (256, 128, 16),        # shortest supported reduction
+    (2048, 16, 384),       # final layer: 16 output columns (one mostly out-of-bounds tile)
+    (16, 1152, 2048),      # its weight gradient: 16 output rows
 ]
 
 
@@ -373,8 +377,11 @@ def test_fused_adamw_ema_matches_torch(ops):
         norm_sq.zero_()
         call("reed_grad_sumsq", g.data_ptr(), n, norm_sq.data_ptr(), st)
         assert _rel(norm_sq.sqrt().float(), total) < 1e-5
+        # odd steps pass the step as a host scalar, even steps through the device counter a CUDA-graph replay reads
+        step_dev = torch.tensor([step], device=DEV, dtype=torch.int32)
         call("reed_adamw_ema", p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), ema.data_ptr(), shadow.data_ptr(),
-             n, norm_sq.data_ptr(), 1.0, 1.0, 1e-3, 0.9, 0.999, 1e-8, 0.01, step, 0.99, st)
+             n, norm_sq.data_ptr(), 1.0, 1.0, 1e-3, 0.9, 0.999, 1e-8, 0.01, step if step % 2 else 0, 0.99,
+             None if step % 2 else step_dev.data_ptr(), st)
         assert float((p - ref_p.data).abs().max()) < 2e-6
         assert float((ema - ema_ref).abs().max()) < 2e-6
         assert torch.equal(shadow, p.bfloat16())

@@ -230,6 +230,51 @@ def test_trainer_step_matches_reference_glue(golden, precision):
         assert torch.equal(b.shadow, b.param.bfloat16())
 
 
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_trainer_graph_replay_matches_eager(precision):
+    """The captured CUDA graph of the train step (loss, backward, clip, AdamW, EMA) reproduces eager stepping:
+    same CPU time draws, same device noise/label-dropout streams, same parameters after every step."""
+    from reed_b200.image.loss import SILoss
+    from reed_b200.image.trainer import ReedTrainer
+    spec = ArchSpec(input_size=16, hidden_size=128, decoder_hidden_size=128, depth=2, num_heads=2, encoder_depth=1,
+                    z_dims=[64], projector_dim=128)
+    sd = random_state(spec, 11)
+    batches = [random_batch(spec, 4, 40 + i) for i in range(5)]
+    to_dev = lambda d: (d["x"].to(DEV), d["y"].to(DEV), [z.to(DEV) for z in d["zs"]])
+
+    def run(graphed):
+        torch.manual_seed(123)
+        torch.cuda.manual_seed(123)
+        model = _build(spec, sd, precision).train()
+        tr = ReedTrainer(model, SILoss(enc_names=["dinov2"], loss_weights={"dinov2": 1.0}), precision=precision)
+        losses = []
+        if graphed:
+            tr.capture(*to_dev(batches[0]), warmup=2)          # two real steps on batch 0
+            for i in range(2, 5):
+                loss, _ = tr.train_step_graphed(*to_dev(batches[i]), diffusion_decay=0.5 + 0.1 * i, repa_decay=0.9)
+                losses.append(float(loss))
+        else:
+            for i in (0, 0, 2, 3, 4):
+                decay = (1.0, 1.0) if i == 0 else (0.5 + 0.1 * i, 0.9)
+                loss, _ = tr.train_step(*to_dev(batches[i]), diffusion_decay=decay[0], repa_decay=decay[1])
+                losses.append(float(loss))
+            losses = losses[2:]
+        assert tr.step_count == 5
+        return losses, {k: v.clone() for k, v in model.state_dict().items()}, {k: v.clone() for k, v in tr.ema.state_dict().items()}
+
+    l_e, p_e, ema_e = run(False)
+    l_g, p_g, ema_g = run(True)
+    tol = 1e-6 if precision == "fp32" else 1e-5     # same kernels on the same data: only atomics ordering differs
+    for a, b in zip(l_e, l_g):
+        assert abs(a - b) <= tol * max(1.0, abs(a)), (l_e, l_g)
+    # Adam normalises the update: where a gradient is ~0 an atomics-ordering difference in its last bits can move a
+    # parameter by a fraction of lr = 1e-4 per step (bf16 mode accumulates bias/modulation gradients with fp32 atomics)
+    ptol = 2e-5 if precision == "fp32" else 2.5e-4
+    for k in p_e:
+        assert float((p_e[k] - p_g[k]).abs().max()) <= ptol, k
+        assert float((ema_e[k] - ema_g[k]).abs().max()) <= ptol, k
+
+
 def test_full_size_properties_xl2_bf16():
     """BASELINE config 3 shapes (SiT-XL/2, T=256, head_dim 72) at a small batch: size-independent properties."""
     from reed_b200.image.loss import SILoss
