@@ -359,11 +359,19 @@ def run_gpu_arm(args, cfg):
             line["cpu_baseline"] = cpu_info
         print(json.dumps(line), flush=True)
     if world > 1:
+        # every rank has finished its collectives; NCCL teardown with a captured graph still alive can block, and
+        # the JSON line is already out, so leave without the communicator destructor
         dist.barrier()
-        dist.destroy_process_group()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def main():
+    if os.environ.get("REED_BENCH_WATCHDOG"):       # debugging aid: dump every thread's Python stack and exit after N s
+        import faulthandler
+        faulthandler.dump_traceback_later(int(os.environ["REED_BENCH_WATCHDOG"]), exit=True)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
