@@ -21,6 +21,7 @@ int gemm_tcgen05(const void* A, int64_t lda, int a_mn, const void* B, int64_t ld
                  int d_dtype, int M, int N, int K, const EpiParams& ep, cudaStream_t st);
 bool gemm_tcgen05_supported(int64_t lda, int64_t ldb, int64_t ldd, const void* A, const void* B, int M, int N, int K);
 void gemm_tcgen05_force_cta_group(int cg);
+void gemm_tcgen05_force_bn(int bn);
 int attn_simt_fwd(int act_dtype, const void* qkv, void* o, float* lse, int B, int T, int H, int hd, cudaStream_t st);
 int attn_simt_bwd(int act_dtype, const void* qkv, const void* o, const void* d_o, const float* lse, void* dqkv,
                   float* delta, int B, int T, int H, int hd, cudaStream_t st);
@@ -28,6 +29,10 @@ int attn_mma_fwd(const void* qkv, void* o, float* lse, int B, int T, int H, int 
 int attn_mma_bwd(const void* qkv, const void* o, const void* d_o, const float* lse, void* dqkv, float* delta, int B,
                  int T, int H, int hd, cudaStream_t st);
 bool attn_mma_supported(int T, int hd);
+int attn_tc5_fwd(const void* qkv, void* o, float* lse, int B, int T, int H, int hd, cudaStream_t st);
+int attn_tc5_bwd(const void* qkv, const void* o, const void* d_o, const float* lse, void* dqkv, float* delta, int B,
+                 int T, int H, int hd, cudaStream_t st);
+bool attn_tc5_supported(int T, int hd);
 
 }  // namespace reed
 
@@ -66,23 +71,47 @@ extern "C" int reed_gemm(int act_dtype, const void* A, int64_t lda, int a_mn_maj
   ep.ld_gate = ld_gate; ep.rows_per_group = rows_per_group > 0 ? rows_per_group : 1; ep.out2 = out2; ep.ld_out2 = ld_out2;
   ep.accumulate = accumulate;
   cudaStream_t st = (cudaStream_t)stream;
+  const int force_bn = backend >> 3;       // test knob: bits 3+ of `backend` pin the tile width (1/2/3 = 128/192/256)
+  backend &= 7;
   const bool tc_ok = act_dtype == kBF16 && gemm_tcgen05_supported(lda, ldb, ldd, A, B, M, N, K) &&
                      (ld_aux % 4 == 0) && (ld_out2 % 4 == 0) && (ld_gate % 4 == 0);
   if (backend >= 2) REED_REQUIRE(tc_ok, "gemm: tcgen05 path required but shape/dtype unsupported (M=%d N=%d K=%d)", M, N, K);
-  if (backend != 1 && tc_ok) {
+  // a weight gradient over a handful of rows (adaLN / embedder linears: the contraction is the batch, K <= 64) is an
+  // outer-product stream that writes M*N floats - the SIMT kernel does it at HBM speed, a 256-wide MMA tile would not
+  const bool tiny_wgrad = a_mn_major && b_mn_major && K <= 64 && d_dtype == kF32 && epilogue == kEpiNone && !bias &&
+                          backend < 2 && N % 4 == 0;
+  if (backend != 1 && tc_ok && !tiny_wgrad) {
     gemm_tcgen05_force_cta_group(backend == 3 ? 1 : (backend == 4 ? 2 : 0));
+    gemm_tcgen05_force_bn(force_bn == 1 ? 128 : (force_bn == 2 ? 192 : (force_bn == 3 ? 256 : 0)));
     return gemm_tcgen05(A, lda, a_mn_major, B, ldb, b_mn_major, D, ldd, d_dtype, M, N, K, ep, st);
   }
   return gemm_simt(act_dtype, A, lda, a_mn_major, B, ldb, b_mn_major, D, ldd, d_dtype, M, N, K, ep, st);
 }
 
 // qkv: [B, T, 3, H, hd] (act dtype); o: [B, T, H, hd]; lse: [B, H, T] fp32
+// backend: 0 auto (tcgen05 kernel when T/hd allow, else mma.sync, else SIMT), 1 force SIMT, 2 require a tensor-core
+// kernel, 3 require the mma.sync kernel, 4 require the tcgen05 kernel
+static int attn_pick(int act_dtype, int T, int hd, int backend, int* which) {
+  const bool tc5_ok = act_dtype == kBF16 && attn_tc5_supported(T, hd);
+  const bool mma_ok = act_dtype == kBF16 && attn_mma_supported(T, hd);
+  if (backend == 4) REED_REQUIRE(tc5_ok, "attention: tcgen05 path required but T=%d hd=%d unsupported", T, hd);
+  if (backend == 3) REED_REQUIRE(mma_ok, "attention: mma.sync path required but T=%d hd=%d unsupported", T, hd);
+  if (backend == 2) REED_REQUIRE(tc5_ok || mma_ok, "attention: tensor-core path required but T=%d hd=%d unsupported", T, hd);
+  if (backend == 1) *which = 0;
+  else if (backend == 3) *which = 1;
+  else if (tc5_ok) *which = 2;
+  else if (mma_ok) *which = 1;
+  else *which = 0;
+  return 0;
+}
+
 extern "C" int reed_attn_fwd(int act_dtype, const void* qkv, void* o, void* lse, int B, int T, int H, int hd,
                              int backend, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
-  const bool mma_ok = act_dtype == kBF16 && attn_mma_supported(T, hd);
-  if (backend == 2) REED_REQUIRE(mma_ok, "attention: tensor-core path required but T=%d hd=%d unsupported", T, hd);
-  if (backend != 1 && mma_ok) return attn_mma_fwd(qkv, o, (float*)lse, B, T, H, hd, st);
+  int which = 0;
+  if (attn_pick(act_dtype, T, hd, backend, &which)) return 1;
+  if (which == 2) return attn_tc5_fwd(qkv, o, (float*)lse, B, T, H, hd, st);
+  if (which == 1) return attn_mma_fwd(qkv, o, (float*)lse, B, T, H, hd, st);
   return attn_simt_fwd(act_dtype, qkv, o, (float*)lse, B, T, H, hd, st);
 }
 
@@ -90,8 +119,9 @@ extern "C" int reed_attn_fwd(int act_dtype, const void* qkv, void* o, void* lse,
 extern "C" int reed_attn_bwd(int act_dtype, const void* qkv, const void* o, const void* d_o, const void* lse,
                              void* dqkv, void* delta, int B, int T, int H, int hd, int backend, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
-  const bool mma_ok = act_dtype == kBF16 && attn_mma_supported(T, hd);
-  if (backend == 2) REED_REQUIRE(mma_ok, "attention: tensor-core path required but T=%d hd=%d unsupported", T, hd);
-  if (backend != 1 && mma_ok) return attn_mma_bwd(qkv, o, d_o, (const float*)lse, dqkv, (float*)delta, B, T, H, hd, st);
+  int which = 0;
+  if (attn_pick(act_dtype, T, hd, backend, &which)) return 1;
+  if (which == 2) return attn_tc5_bwd(qkv, o, d_o, (const float*)lse, dqkv, (float*)delta, B, T, H, hd, st);
+  if (which == 1) return attn_mma_bwd(qkv, o, d_o, (const float*)lse, dqkv, (float*)delta, B, T, H, hd, st);
   return attn_simt_bwd(act_dtype, qkv, o, d_o, (const float*)lse, dqkv, (float*)delta, B, T, H, hd, st);
 }

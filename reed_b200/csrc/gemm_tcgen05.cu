@@ -62,7 +62,12 @@ static int sm_count() {
 // 12-13 TB/s chip-wide measured here) - the larger of the two paces the tile; DP pays whole waves.
 struct GemmPlan { int cg, bn, stream_k, grid; };
 
-static GemmPlan plan_gemm(int M, int N, int K, int b_mn, bool sk_ok, int force_cg) {
+// mirrors half_tile_ok<CG, BN, B_MN>() of the kernel
+static bool half_tile_ok(int cg, int bn, int b_mn) {
+  return b_mn ? ((bn / 2 / cg) % 64 == 0) : ((bn / 2 / cg) % 8 == 0 && (bn / 2) % 16 == 0);
+}
+
+static GemmPlan plan_gemm(int M, int N, int K, int b_mn, bool sk_ok, int force_cg, int force_bn) {
   const int ctas = sm_count();
   const int num_kb = ceil_div(K, 64);
   GemmPlan best{1, 128, 0, 1};
@@ -73,20 +78,36 @@ static GemmPlan plan_gemm(int M, int N, int K, int b_mn, bool sk_ok, int force_c
     const int workers = ctas / cg;
     for (int bn : {256, 192, 128}) {
       if (b_mn && (bn / cg) % 64 != 0) continue;
-      const int tiles = ceil_div(M, 128 * cg) * ceil_div(N, bn);
+      if (force_bn && bn != force_bn) continue;
+      const int tiles_m = ceil_div(M, 128 * cg), tiles_n = ceil_div(N, bn);
+      const int tiles = tiles_m * tiles_n;
       const double per_kb = fmax(2.0 * bn, (16384.0 + (bn / cg) * 128.0) / 42.0);
+      const double per_kb_half = fmax(1.0 * bn, (16384.0 + (bn / cg) * 128.0) / 42.0);
       const double tile_cost = num_kb * per_kb + 1500.0;     // + pipeline fill / non-overlapped epilogue tail
-      const double waves = (double)ceil_div(tiles, workers);
-      const double dp_cost = waves * tile_cost;
+      const double half_cost = num_kb * per_kb_half + 1000.0;
+      // data-parallel makespan under the kernel's order: full tiles, then the ragged half-width column, snake rounds
+      const bool ragged = half_tile_ok(cg, bn, b_mn) && (N - (tiles_n - 1) * bn) <= bn / 2;
+      const int count_full = tiles_m * (tiles_n - (ragged ? 1 : 0));
+      const int used = tiles < workers ? tiles : workers;
+      double dp_cost = 0.0;
+      for (int w = 0; w < used; ++w) {
+        double load = 0.0;
+        for (int r = 0;; ++r) {
+          const int v = r * used + ((r & 1) ? used - 1 - w : w);
+          if (v >= tiles) break;
+          load += v < count_full ? tile_cost : half_cost;
+        }
+        dp_cost = fmax(dp_cost, load);
+      }
       double cost = dp_cost;
       int sk = 0;
-      if (sk_ok && (int64_t)tiles * num_kb >= (int64_t)workers * 8) {
+      if (sk_ok && (int64_t)tiles * num_kb >= (int64_t)workers * 4) {
         const double sk_cost = (double)tiles / workers * tile_cost + 3000.0;   // extra partial-tile epilogues
         if (sk_cost < 0.93 * dp_cost) { cost = sk_cost; sk = 1; }
       }
       if (cost < best_cost) {
         best_cost = cost;
-        best = GemmPlan{cg, bn, sk, sk ? workers * cg : (tiles < workers ? tiles : workers) * cg};
+        best = GemmPlan{cg, bn, sk, sk ? workers * cg : used * cg};
       }
     }
   }
@@ -94,13 +115,15 @@ static GemmPlan plan_gemm(int M, int N, int K, int b_mn, bool sk_ok, int force_c
 }
 
 static int g_force_cg = 0;   // test/debug knob (reed_gemm backend codes 3 / 4): force cta_group::1 / ::2
+static int g_force_bn = 0;   // test knob: pin the tile width
 void gemm_tcgen05_force_cta_group(int cg) { g_force_cg = cg; }
+void gemm_tcgen05_force_bn(int bn) { g_force_bn = bn; }
 
 int gemm_tcgen05(const void* A, int64_t lda, int a_mn, const void* B, int64_t ldb, int b_mn, void* D, int64_t ldd,
                  int d_dtype, int M, int N, int K, const EpiParams& ep, cudaStream_t st) {
   // stream-K needs an output that tolerates fp32 atomics: no epilogue, no bias, fp32 D (the weight gradients)
   const bool sk_ok = ep.kind == kEpiNone && d_dtype == kF32 && ep.bias == nullptr && ep.out2 == nullptr;
-  const GemmPlan p = plan_gemm(M, N, K, b_mn, sk_ok, g_force_cg);
+  const GemmPlan p = plan_gemm(M, N, K, b_mn, sk_ok, g_force_cg, g_force_bn);
   if (p.stream_k && !ep.accumulate)
     REED_CHECK_CUDA(cudaMemset2DAsync(D, (size_t)ldd * 4, 0, (size_t)N * 4, (size_t)M, st));
 

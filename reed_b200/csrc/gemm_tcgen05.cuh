@@ -22,207 +22,16 @@
 #include <cuda.h>
 #include <stdlib.h>
 #include "common.cuh"
+#include "tcgen05_ptx.cuh"
 
 namespace reed {
 
 constexpr int BM = 128;         // accumulator rows per CTA (UMMA M = 128 x CG)
 constexpr int BK = 64;          // 64 bf16 = 128 B = one swizzle row
-constexpr int UMMA_K = 16;
 constexpr int kGemmThreads = 384;   // warps 0-3: TMA / MMA / TMEM alloc / spare; warps 4-11: epilogue
 constexpr int kEpiWarps = 8;
 constexpr int kStageCols = 32;  // accumulator columns moved per tcgen05.ld
 constexpr int kStagePitch = 36; // floats; 144 B row pitch keeps float4 smem accesses conflict-free
-
-// ------------------------------------------------------------------------------------------------
-// PTX wrappers
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  const uint32_t addr = smem_u32(bar);
-  uint32_t done = 0;
-  uint64_t spins = 0;
-  while (true) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(addr), "r"(parity)
-        : "memory");
-    if (done) break;
-    if (++spins > (1ull << 26)) {   // ~seconds: a protocol bug must surface as an error, never as a hung GPU
-      printf("reed gemm: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
-      __trap();
-    }
-  }
-}
-__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
-      : "memory");
-}
-// cta_group::2: the executing CTA's TMA lands in its own smem but reports its bytes to the LEADER CTA's mbarrier
-// (`bar_cluster_addr` = shared::cluster address of that barrier, from mapa)
-__device__ __forceinline__ void tma_load_2d_cg2(const CUtensorMap* map, uint32_t bar_cluster_addr, void* dst, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(smem_u32(dst)), "l"(map), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
-      : "memory");
-}
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-// shared::cluster address of the same smem variable in CTA `rank` of this cluster
-__device__ __forceinline__ uint32_t mapa_u32(uint32_t local_addr, uint32_t rank) {
-  uint32_t r;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
-  return r;
-}
-__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster_addr) {
-  // relaxed: the barrier orders TMEM reuse (tcgen05.wait::ld + tcgen05.fence precede it), not global memory, so the
-  // arrive need not wait for this warp's outstanding global stores (a release at cluster scope would)
-  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
-}
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
-  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
-}
-
-// CG = 1: one CTA; CG = 2: a CTA pair (both CTAs' allocator warps execute the cta_group::2 forms)
-template <int CG>
-__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t cols) {
-  if constexpr (CG == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(cols)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  } else {
-    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(cols)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
-  }
-}
-template <int CG>
-__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
-  if constexpr (CG == 1)
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
-  else
-    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
-}
-template <int CG>
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
-                                          uint32_t accumulate) {
-  if constexpr (CG == 1)
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-        : "memory");
-  else
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-// mbarrier arrives once every previously issued tcgen05.mma of this thread has completed; with CG = 2 the arrive is
-// multicast to the barrier at the same smem offset in both CTAs of the pair
-template <int CG>
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  if constexpr (CG == 1)
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
-                 : "memory");
-  else
-    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-                 ::"r"(smem_u32(bar)), "h"((uint16_t)3)
-                 : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
-  uint32_t* r = reinterpret_cast<uint32_t*>(v);
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr)
-      : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-
-// Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout), SWIZZLE_128B, version 1.
-//   K-major : rows of 128 B, 8-row swizzle atoms 1024 B apart            -> SBO = 1024, LBO unused
-//   MN-major: each TMA box is 64 (mn) x BK (k) elements: k-rows of 128 B, -> SBO = 1024 (next 8 k-rows),
-//             the next 64 mn-elements live in the next box               -> LBO = BK * 128 B
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
-  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
-  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
-  d |= (uint64_t)1 << 46;   // descriptor version (Blackwell)
-  d |= (uint64_t)2 << 61;   // SWIZZLE_128B
-  return d;
-}
-
-// cute::UMMA::InstrDescriptor: D fp32, A/B bf16, dense
-__host__ __device__ constexpr uint32_t make_idesc(int m, int n, int a_mn, int b_mn) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) |
-         ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
-}
-
-// ------------------------------------------------------------------------------------------------
-// fast epilogue math (bf16 tensor-core mode only; the fp32 mode runs the SIMT kernel with precise math)
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ float tanh_fast(float x) {
-  float y;
-  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-__device__ __forceinline__ float gelu_fast(float x) {
-  const float k0 = 0.7978845608028654f, k1 = 0.044715f;
-  return 0.5f * x * (1.f + tanh_fast(k0 * (x + k1 * x * x * x)));
-}
-__device__ __forceinline__ float gelu_grad_fast(float x) {
-  const float k0 = 0.7978845608028654f, k1 = 0.044715f;
-  const float x2 = x * x;
-  const float th = tanh_fast(k0 * (x + k1 * x * x2));
-  return 0.5f * (1.f + th) + 0.5f * x * (1.f - th * th) * (k0 * (1.f + 3.f * k1 * x2));
-}
-__device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
-__device__ __forceinline__ float silu_fast(float x) { return x * sigmoid_fast(x); }
-__device__ __forceinline__ float silu_grad_fast(float x) {
-  const float s = sigmoid_fast(x);
-  return s * (1.f + x * (1.f - s));
-}
-__device__ __forceinline__ float round_bf16(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
-__device__ __forceinline__ void red_add4(float* p, const F4& f) {
-  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(f.v[0]), "f"(f.v[1]), "f"(f.v[2]), "f"(f.v[3])
-               : "memory");
-}
 
 constexpr int kEpiAccum = 6;    // internal: kEpiNone with ep.accumulate (D += acc), fp32 D
 constexpr int kEpiAtomic = 7;   // internal: stream-K partial tile, red.add into fp32 D
@@ -244,24 +53,33 @@ struct GemmCfg {
 // outputs, i.e. the weight-gradient GEMMs whose tile count does not fill 148 SMs evenly): the (tile, k-block) units
 // are cut into gridDim.x equal contiguous ranges; a CTA reduces each piece of a tile it owns in TMEM and adds it
 // into the zero-initialised (or accumulating) fp32 output with vector red.global.add.
-struct Seg { int tile, kb0, kb1; };
+struct Seg { int tile, kb0, kb1, half; };   // half: the tile is the ragged last column tile, computed BN/2 wide
 struct Sched {
-  int sk, num_tiles, num_kb, tile;
+  int sk, num_tiles, num_kb, tiles_n, ragged, round;
   int64_t u, u_end;
-  int stride;
-  // `worker` = index of this CTA (CG = 1) or CTA pair (CG = 2) among `workers`
-  __device__ Sched(int sk_, int num_tiles_, int num_kb_, int worker, int workers)
-      : sk(sk_), num_tiles(num_tiles_), num_kb(num_kb_), stride(workers) {
-    tile = worker;
+  int worker, stride;
+  // `worker` = index of this CTA (CG = 1) or CTA pair (CG = 2) among `workers`.
+  // Data-parallel order: all full-width tiles first (row-major), then the ragged last-column tiles (when N leaves a
+  // remainder of at most BN/2 they are computed with a BN/2-wide MMA and cost half a tile); rounds alternate
+  // direction over the workers (snake), so the half tiles of the last rounds land on the workers that got one
+  // tile less - e.g. N = 1152, BN = 256, M = 8192: 128 full + 32 half tiles on 74 pairs take 2 tile times, not 3.
+  __device__ Sched(int sk_, int tiles_m, int tiles_n_, int ragged_, int num_kb_, int worker_, int workers)
+      : sk(sk_), num_tiles(tiles_m * tiles_n_), num_kb(num_kb_), tiles_n(tiles_n_), ragged(ragged_), round(0),
+        worker(worker_), stride(workers) {
     const int64_t total = (int64_t)num_tiles * num_kb;
     u = total * worker / workers;
     u_end = total * (worker + 1) / workers;
   }
   __device__ bool next(Seg& s) {
     if (!sk) {
-      if (tile >= num_tiles) return false;
-      s.tile = tile; s.kb0 = 0; s.kb1 = num_kb;
-      tile += stride;
+      const int v = round * stride + ((round & 1) ? stride - 1 - worker : worker);
+      if (v >= num_tiles) return false;
+      ++round;
+      const int n_full = tiles_n - ragged;
+      const int count_full = (num_tiles / tiles_n) * n_full;
+      if (v < count_full) { s.tile = (v / n_full) * tiles_n + (v % n_full); s.half = 0; }
+      else { s.tile = (v - count_full) * tiles_n + tiles_n - 1; s.half = 1; }
+      s.kb0 = 0; s.kb1 = num_kb;
       return true;
     }
     if (u >= u_end) return false;
@@ -269,11 +87,17 @@ struct Sched {
     const int kb0 = (int)(u - (int64_t)t * num_kb);
     const int64_t left = u_end - u;
     const int len = (num_kb - kb0) < left ? (num_kb - kb0) : (int)left;
-    s.tile = t; s.kb0 = kb0; s.kb1 = kb0 + len;
+    s.tile = t; s.kb0 = kb0; s.kb1 = kb0 + len; s.half = 0;
     u += len;
     return true;
   }
 };
+
+// the ragged last column tile may run BN/2 wide when every CTA's share of it is still a whole number of TMA boxes
+template <int CG, int BN, int B_MN>
+__host__ __device__ constexpr bool half_tile_ok() {
+  return B_MN ? ((BN / 2 / CG) % 64 == 0) : ((BN / 2 / CG) % 8 == 0 && (BN / 2) % 16 == 0);
+}
 
 // One epilogue warp's share of one accumulator tile: TMEM lane quadrant q (32 rows), every second 32-column chunk.
 // Per chunk: tcgen05.ld (thread = row) -> smem transpose -> row-coalesced fused epilogue.  Everything a chunk needs
@@ -316,7 +140,7 @@ __device__ __forceinline__ void epilogue_tile(const EpiParams& ep, TD* __restric
     if (col < N) {
       if (ep.bias != nullptr) b4 = __ldg(reinterpret_cast<const float4*>(ep.bias + col));
       if constexpr (KIND == kEpiGateRes) {
-        if (g_uniform) g4 = __ldg(reinterpret_cast<const float4*>(ep.gate + (int64_t)g_first * ep.ld_gate + col));
+        if (g_uniform && row_base < M) g4 = __ldg(reinterpret_cast<const float4*>(ep.gate + (int64_t)g_first * ep.ld_gate + col));
       }
       if constexpr (kAuxF32 || kAuxBf16) {
 #pragma unroll
@@ -430,8 +254,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   const bool leader = rank == 0;
   const int worker = blockIdx.x / CG, workers = gridDim.x / CG;
   const int tiles_m = (M + BMT - 1) / BMT, tiles_n = (N + BN - 1) / BN;
-  const int num_tiles = tiles_m * tiles_n;
   const int num_kb = (K + BK - 1) / BK;
+  const int n_rem = N - (tiles_n - 1) * BN;    // width of the last column tile
+  const int ragged = (!stream_k && half_tile_ok<CG, BN, B_MN>() && n_rem <= BN / 2) ? 1 : 0;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_a);
@@ -459,11 +284,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     // ============================== TMA producer (every CTA loads its own A rows / B rows) ==============================
     int stage = 0;
     uint32_t phase = 0;
-    Sched sched(stream_k, num_tiles, num_kb, worker, workers);
+    Sched sched(stream_k, tiles_m, tiles_n, ragged, num_kb, worker, workers);
     Seg sg;
     while (!(dbg & 1) && sched.next(sg)) {
       const int m0 = (sg.tile / tiles_n) * BMT + (int)rank * BM;
-      const int n0 = (sg.tile % tiles_n) * BN + (int)rank * BNL;
+      // a half tile is BN/2 wide: each CTA of the pair supplies BN/2/CG rows of B, taken from the head of its box
+      const int n0 = (sg.tile % tiles_n) * BN + (int)rank * (sg.half ? BNL / 2 : BNL);
       for (int kb = sg.kb0; kb < sg.kb1; ++kb) {
         mbar_wait(&empty[stage], phase ^ 1);
         uint8_t* sa = stage_base + stage * Cfg::kStageBytes;
@@ -504,17 +330,19 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     }
   } else if (warp == 1 && lane == 0 && leader) {
     // ============================== MMA issuer (leader CTA only) ==============================
-    constexpr uint32_t idesc = make_idesc(BMT, BN, A_MN, B_MN);
+    constexpr uint32_t idesc_full = make_idesc(BMT, BN, A_MN, B_MN);
+    constexpr uint32_t idesc_half = make_idesc(BMT, BN / 2, A_MN, B_MN);
     int stage = 0;
     uint32_t phase = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
-    Sched sched(stream_k, num_tiles, num_kb, worker, workers);
+    Sched sched(stream_k, tiles_m, tiles_n, ragged, num_kb, worker, workers);
     Seg sg;
     while (sched.next(sg)) {
       mbar_wait(&tempty[acc], acc_phase ^ 1);
       tc_fence_after();
       const uint32_t tmem_d = tmem_base + acc * BN;
+      const uint32_t idesc = sg.half ? idesc_half : idesc_full;
       for (int kb = sg.kb0; kb < sg.kb1; ++kb) {
         if (!(dbg & 1)) mbar_wait(&full[stage], phase);
         tc_fence_after();
@@ -542,7 +370,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     float* st = staging + (warp - 4) * 32 * kStagePitch;
     int acc = 0;
     uint32_t acc_phase = 0;
-    Sched sched(stream_k, num_tiles, num_kb, worker, workers);
+    Sched sched(stream_k, tiles_m, tiles_n, ragged, num_kb, worker, workers);
     Seg sg;
     while (sched.next(sg)) {
       const int m0 = (sg.tile / tiles_n) * BMT + (int)rank * BM, n0 = (sg.tile % tiles_n) * BN;

@@ -139,15 +139,16 @@ class SiTBlock(nn.Module):
         self.mlp = _MlpParams(hidden_size, int(hidden_size * mlp_ratio))
         self.adaLN_modulation = nn.Sequential(nn.SiLU(), nn.Linear(hidden_size, 6 * hidden_size, bias=True))
 
-    def forward(self, x, c_act, act_dtype):
-        """x: (N,T,D) fp32; c_act = silu(c) already in the act dtype (shared by every block)."""
+    def forward(self, x, c_act, act_dtype, c_acc=None):
+        """x: (N,T,D) fp32; c_act = silu(c) already in the act dtype (shared by every block); c_acc: the side
+        accumulator the block adds its gradient w.r.t. c_act into (ops.silu_cast)."""
         if self.qk_norm:
             raise NotImplementedError("qk_norm=True is not wired to the CUDA attention kernels yet")
         lin = self.adaLN_modulation[1]
         a, m = self.attn, self.mlp
         return ops.SiTBlockFn.apply(x, c_act, lin.weight, lin.bias, a.qkv.weight, a.qkv.bias, a.proj.weight, a.proj.bias,
                                     m.fc1.weight, m.fc1.bias, m.fc2.weight, m.fc2.bias, self.num_heads, act_dtype,
-                                    getattr(self, "_reed_after_backward", None))
+                                    getattr(self, "_reed_after_backward", None), c_acc)
 
 
 class FinalLayer(nn.Module):
@@ -266,13 +267,13 @@ class SiT(nn.Module):
         width = tok.shape[-1]
 
         c = self.t_embedder(t, act_dtype) + self.y_embedder(y, self.training)
-        c_act = ops.SiluCastFn.apply(c, act_dtype)
+        c_act, c_acc = ops.silu_cast(c, act_dtype)
 
         split = self.encoder_depth_text is not None and self.encoder_depth_text != self.encoder_depth
         zs = None
         z_img = z_txt = None
         for i, blk in enumerate(self.blocks, start=1):
-            tok = blk(tok, c_act, act_dtype)
+            tok = blk(tok, c_act, act_dtype, c_acc)
             if inference:
                 continue
             if i == self.encoder_depth:

@@ -44,6 +44,14 @@ class Bucket:
         self.numel += (p.numel() + _ALIGN - 1) // _ALIGN * _ALIGN
 
 
+class _ZeroGroup:
+    """The contiguous gradient region of a bucket's 1-D parameters and whether it was zeroed this step."""
+
+    def __init__(self, view):
+        self.view = view
+        self.zeroed = False
+
+
 class FlatState:
     """Re-homes a model's parameters into flat per-bucket storage (works on any device; kernels need CUDA)."""
 
@@ -62,7 +70,10 @@ class FlatState:
                 self.buckets.append(by_key[key])
             return by_key[key]
 
-        for name, p in model.named_parameters():
+        # within a bucket the 1-D parameters (biases) come first and contiguous: their gradients are accumulated
+        # into (column sums, atomics) and are zeroed with ONE fill per bucket on first touch (ops._zero_fresh)
+        named = list(model.named_parameters())
+        for name, p in [(n, q) for n, q in named if q.dim() == 1] + [(n, q) for n, q in named if q.dim() != 1]:
             if not p.requires_grad:
                 self.frozen.append((p, ema_params.get(name)))
                 continue
@@ -99,6 +110,11 @@ class FlatState:
                     eview = b.ema[off:off + n].view(p.shape)
                     eview.copy_(p.data)                      # update_ema(ema, model, decay=0)
                     ep.data = eview
+            n1d = sum((p.numel() + _ALIGN - 1) // _ALIGN * _ALIGN for p in b.params if p.dim() == 1)
+            b.zero_group = _ZeroGroup(b.grad[:n1d])
+            for p in b.params:
+                if p.dim() == 1 and p._reed_kernel_grad:
+                    p._reed_zero_group = b.zero_group
         for p, ep in self.frozen:
             if ep is not None:
                 ep.data.copy_(p.data)
@@ -110,6 +126,7 @@ class FlatState:
         gradients that arrive through autograd (the label-embedding table) are zeroed and accumulated into."""
         for b in self.buckets:
             b.work = None
+            b.zero_group.zeroed = False
             for p, off in zip(b.params, b.offsets):
                 if p._reed_kernel_grad:
                     p._reed_grad_fresh = True

@@ -213,13 +213,24 @@ def _weight_grad(p, dy2d, x2d):
     return gemm(dy2d, x2d, a_mn=True, b_mn=True, out_dtype=torch.float32).view(p.shape)
 
 
+def _zero_fresh(p, main):
+    """First touch of an accumulate-into gradient this step: zero it - together with every other 1-D gradient of the
+    same bucket when the trainer laid them out contiguously (one fill per block instead of five)."""
+    grp = getattr(p, "_reed_zero_group", None)
+    if grp is None:
+        main.zero_()
+    elif not grp.zeroed:
+        grp.view.zero_()
+        grp.zeroed = True
+
+
 def _bias_grad(p, dy2d):
     if p is None:
         return None
     main, acc = _grad_target(p)
     if main is not None:
         if not acc:
-            main.zero_()
+            _zero_fresh(p, main)
         colsum(dy2d, main)
         return None
     out = torch.zeros(dy2d.shape[1], device=dy2d.device, dtype=torch.float32)
@@ -269,6 +280,19 @@ def linear(x, weight, bias, *, act=ACT_NONE, act_dtype, out_dtype=None):
     return LinearFn.apply(x, weight, bias, act, act_dtype, out_dtype if out_dtype is not None else act_dtype)
 
 
+class _GradAccumulator:
+    """fp32 side buffer the consumers of a shared tensor add their input gradients into (one stream-K GEMM each),
+    instead of handing autograd 28 separate bf16 gradients to sum."""
+
+    def __init__(self):
+        self.buf = None
+
+    def get(self, like, dtype=torch.float32):
+        if self.buf is None:
+            self.buf = torch.zeros(like.shape, device=like.device, dtype=dtype)
+        return self.buf
+
+
 class SiluCastFn(torch.autograd.Function):
     """silu(c) emitted in the act dtype (the shared input of every adaLN linear, sit.py:125-133,148-154)."""
 
@@ -276,12 +300,27 @@ class SiluCastFn(torch.autograd.Function):
     def forward(ctx, c, act_dtype):
         _require_cuda(c)
         ctx.save_for_backward(c)
-        return cast(c, act_dtype, op=1)
+        out = cast(c, act_dtype, op=1)
+        ctx.acc = _GradAccumulator()
+        return out
 
     @staticmethod
     def backward(ctx, dy):
         (c,) = ctx.saved_tensors
-        return act_bwd(cast(dy.contiguous(), torch.float32), c, ACT_SILU), None
+        dy = cast(dy.contiguous(), torch.float32)
+        if ctx.acc.buf is not None:          # gradients the transformer blocks accumulated on the side
+            total = torch.empty_like(dy)
+            _launch("reed_add_f32", _p(dy), _p(ctx.acc.buf), _p(total), dy.numel(), _stream())
+            dy = total
+            ctx.acc.buf = None
+        return act_bwd(dy, c, ACT_SILU), None
+
+
+def silu_cast(c, act_dtype):
+    """Returns (silu(c) in act dtype, accumulator the blocks add their dL/d silu(c) into)."""
+    out = SiluCastFn.apply(c, act_dtype)
+    acc = out.grad_fn.acc if out.grad_fn is not None and hasattr(out.grad_fn, "acc") else None
+    return out, acc
 
 
 class CastFn(torch.autograd.Function):
@@ -353,7 +392,7 @@ class SiTBlockFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, c_act, w_ada, b_ada, w_qkv, b_qkv, w_proj, b_proj, w_fc1, b_fc1, w_fc2, b_fc2, num_heads,
-                act_dtype, after_backward):
+                act_dtype, after_backward, c_acc=None):
         _require_cuda(x, c_act)
         B, T, D = x.shape
         M = B * T
@@ -382,6 +421,7 @@ class SiTBlockFn(torch.autograd.Function):
         ctx.dims = (B, T, D, H, hd)
         ctx.act_dtype = act_dtype
         ctx.after_backward = after_backward
+        ctx.c_acc = c_acc
         return x2.view(B, T, D)
 
     @staticmethod
@@ -403,7 +443,7 @@ class SiTBlockFn(torch.autograd.Function):
             main, acc = _grad_target(p)
             if main is not None:
                 if not acc:
-                    main.zero_()
+                    _zero_fresh(p, main)
                 return main, None
             buf = torch.zeros(p.shape, device=p.device, dtype=torch.float32)
             return buf, buf
@@ -431,11 +471,16 @@ class SiTBlockFn(torch.autograd.Function):
         dmod_a = cast(dmod, act_dtype)
         db_ada = _bias_grad(b_ada, dmod)
         dw_ada = _weight_grad(w_ada, dmod_a, c_act)
-        dc = gemm(dmod_a, W(w_ada), b_mn=True, out_dtype=act_dtype) if ctx.needs_input_grad[1] else None
+        dc = None
+        if ctx.needs_input_grad[1]:
+            if ctx.c_acc is not None:     # [B, 6D] x [6D, D]: few rows, long reduction -> stream-K adds into the side buffer
+                gemm(dmod_a, W(w_ada), b_mn=True, out=ctx.c_acc.get(c_act), accumulate=True)
+            else:
+                dc = gemm(dmod_a, W(w_ada), b_mn=True, out_dtype=act_dtype)
 
         if ctx.after_backward is not None:
             ctx.after_backward()
-        return (dx0.view(B, T, D), dc, dw_ada, db_ada, dwqkv, dbqkv, dwp, dbp, dw1, db1, dw2, db2, None, None, None)
+        return (dx0.view(B, T, D), dc, dw_ada, db_ada, dwqkv, dbqkv, dwp, dbp, dw1, db1, dw2, db2, None, None, None, None)
 
 
 # --------------------------------------------------------------------------------------------------

@@ -119,6 +119,28 @@ def test_gemm_epilogues(ops, mode):
         assert _rel(got.float(), want) < tol
 
 
+@pytest.mark.parametrize("cg", [1, 2])
+@pytest.mark.parametrize("bn", [1, 2, 3])                      # tile width 128 / 192 / 256
+@pytest.mark.parametrize("layout", [(0, 0), (0, 1), (1, 1)])
+@pytest.mark.parametrize("shape", [(2560, 1152, 192), (1024, 1096, 320), (700, 320, 128), (512, 64, 256)])
+def test_gemm_ragged_last_column_tile(ops, shape, layout, bn, cg):
+    """N leaves a remainder of at most half a tile: the last column tile runs as a half-width MMA (each CTA of a pair
+    supplies a quarter tile of B) and the tiles are dealt in snake order.  Every (cta_group, BN, layout) is pinned."""
+    M, N, K = shape
+    a_mn, b_mn = layout
+    if (a_mn and M % 8) or (b_mn and N % 8):
+        pytest.skip("TMA needs 16-byte row pitches")
+    ops.set_backends(gemm={1: ops.BACKEND_TENSOR_CG1, 2: ops.BACKEND_TENSOR_CG2}[cg] + 8 * bn)
+    a, b, a_s, b_s = _operands(M, N, K, a_mn, b_mn, torch.bfloat16)
+    ref = a.float() @ b.float().t()
+    bias = _rand(N, seed=3)
+    out = ops.gemm(a_s, b_s, a_mn=bool(a_mn), b_mn=bool(b_mn), out_dtype=torch.float32, bias=bias)
+    torch.cuda.synchronize()
+    assert _rel(out, ref + bias) < 2e-5, (shape, layout, bn, cg)
+    out_bf = ops.gemm(a_s, b_s, a_mn=bool(a_mn), b_mn=bool(b_mn), out_dtype=torch.bfloat16)
+    assert _rel(out_bf.float(), ref) < 1e-2
+
+
 @pytest.mark.parametrize("cg", [0, 1, 2])
 @pytest.mark.parametrize("shape", [(1152, 1152, 8192), (3456, 1152, 4096), (1152, 4608, 2048), (384, 1536, 8192)])
 def test_gemm_stream_k_wgrad(ops, shape, cg):
@@ -277,6 +299,34 @@ def test_attention_fwd_bwd(ops, cfg, dtype):
     ref.backward(d_o.float())
     dqkv = ops.attention_bwd(qkv, o, d_o, lse, B, T, H, hd)
     assert _rel(dqkv.float(), ref_in.grad) < (2e-5 if dtype == torch.float32 else 2e-2)
+
+
+@pytest.mark.parametrize("backend", [3, 4])                    # 3 = mma.sync kernels, 4 = tcgen05/TMEM kernels
+@pytest.mark.parametrize("cfg", [(2, 256, 3, 64), (3, 256, 2, 72), (2, 128, 2, 64), (1, 128, 3, 72), (32, 256, 16, 72)])
+def test_attention_tensor_core_kernels(ops, cfg, backend):
+    """Both tensor-core attention implementations against fp32 torch attention on the same bf16 inputs; the tcgen05
+    kernels must also agree closely with the mma.sync ones (same bf16 P, fp32 accumulation)."""
+    B, T, H, hd = cfg
+    qkv = _rand(B * T, 3 * H * hd, dtype=torch.bfloat16, seed=1)
+    d_o = _rand(B * T, H * hd, dtype=torch.bfloat16, seed=2)
+    ops.set_backends(attention=backend)
+    o, lse = ops.attention_fwd(qkv, B, T, H, hd)
+    dqkv = ops.attention_bwd(qkv, o, d_o, lse, B, T, H, hd)
+    torch.cuda.synchronize()
+    ops.set_backends()
+    ref_in = qkv.float().requires_grad_(True)
+    ref = _attention_reference(ref_in, B, T, H, hd)
+    assert _rel(o.float(), ref) < 1.2e-2
+    ref.backward(d_o.float())
+    assert _rel(dqkv.float(), ref_in.grad) < 2e-2
+    # per-slice check so that a wrong dq / dk / dv block cannot hide behind the largest one
+    g = ref_in.grad.view(B * T, 3, H * hd)
+    got = dqkv.float().view(B * T, 3, H * hd)
+    for i in range(3):
+        assert _rel(got[:, i], g[:, i]) < 2e-2, i
+    q, k = ref_in.detach().view(B, T, 3, H, hd)[:, :, 0], ref_in.detach().view(B, T, 3, H, hd)[:, :, 1]
+    s = torch.einsum("bthd,bshd->bhts", q, k) * hd ** -0.5
+    assert float((lse - torch.logsumexp(s, dim=-1)).abs().max()) < 2e-3
 
 
 # ---------------------------------------------------------------------------------------------------------
