@@ -2,8 +2,13 @@
 import csv, subprocess, sys
 rep = sys.argv[1]
 topn = int(sys.argv[2]) if len(sys.argv) > 2 else 30
-out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+# extra arguments select a kernel, e.g. --kernel-name regex:dkv --launch-skip 0 --launch-count 1
+out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"] + sys.argv[3:], capture_output=True, text=True).stdout
 rows = list(csv.reader(out.splitlines()))
+ends = [i for i, r in enumerate(rows) if r and r[0] == "Kernel Name"]
+if len(ends) > 1:
+    rows = rows[:ends[1]]
+print(rows[0][1][:120])
 hdr = rows[1]; ix = {h: i for i, h in enumerate(hdr)}
 data = rows[2:]
 tot = sum(int(r[ix['# Samples']]) for r in data)
