@@ -277,55 +277,76 @@ def run_gpu_arm(args, cfg):
     e2e_ms = timed(e2e_step, args.steps)
     e2e_value = world * B * args.steps / (e2e_ms / 1e3)
 
-    # ---- dominant kernel: CUDA events around every GEMM launch of two more steps -------------------------------
+    # ---- dominant kernel: every tcgen05 GEMM launch of one step, re-issued back to back inside a CUDA graph and timed
+    # with CUDA events on the launching stream (an eager step is host-bound, so events around single launches would
+    # time Python, not the kernel).  achieved = sum of algorithmic 2*M*N*K / summed launch time.
     roof = None
-    if rank == 0:
-        records = []
-        real_gemm = ops.gemm
+    records = []
+    real_gemm = ops.gemm
 
-        def probed(a, b, **kw):
-            M, K = (a.shape[1], a.shape[0]) if kw.get("a_mn") else (a.shape[0], a.shape[1])
-            N = b.shape[1] if kw.get("b_mn") else b.shape[0]
-            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            s.record()
-            out = real_gemm(a, b, **kw)
-            e.record()
-            tensor_path = a.dtype == torch.bfloat16 and K >= 64 and N >= 64 and a.stride(0) % 8 == 0 and b.stride(0) % 8 == 0
-            records.append((2.0 * M * N * K, s, e, tensor_path))
-            return out
+    def recording(a, b, **kw):
+        out = real_gemm(a, b, **kw)
+        M, K = (a.shape[1], a.shape[0]) if kw.get("a_mn") else (a.shape[0], a.shape[1])
+        N = b.shape[1] if kw.get("b_mn") else b.shape[0]
+        tensor_path = (a.dtype == torch.bfloat16 and K >= 64 and N >= 64 and a.stride(0) % 8 == 0 and b.stride(0) % 8 == 0
+                       and not (kw.get("a_mn") and kw.get("b_mn") and K <= 64))
+        if tensor_path:
+            kw2 = dict(kw)
+            kw2["out"] = out
+            records.append((2.0 * M * N * K, a, b, kw2))
+        return out
+
     def eager_step(i):
         x, y, zs = resident[i % n_buf]
         trainer.train_step(x, y, zs)
 
     if world > 1:
         dist.barrier()
-    if rank == 0:
-        ops.gemm = probed
-        try:
-            for i in range(2):
-                eager_step(i)
-            torch.cuda.synchronize()
-        finally:
-            ops.gemm = real_gemm
-        tc = [(f, s.elapsed_time(e)) for f, s, e, tp in records if tp]
-        flops, tms = sum(f for f, _ in tc), sum(t for _, t in tc)
+    ops.gemm = recording
+    try:
+        eager_step(0)                      # every rank runs it so the collectives stay matched
+        torch.cuda.synchronize()
+    finally:
+        ops.gemm = real_gemm
+    if rank == 0 and records:
+        reps = 3
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _, a, b, kw in records[:8]:
+                real_gemm(a, b, **kw)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            for _, a, b, kw in records:
+                real_gemm(a, b, **kw)
+        graph.replay()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            graph.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        tms = e0.elapsed_time(e1) / reps
+        flops = sum(r[0] for r in records)
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         except Exception:
             pass
-        peak = peaks.get("bf16_tflops_sustained") or 1400.2
+        peak = peaks.get("bf16_tflops_sustained") or 1400.0
         achieved = flops / (tms * 1e-3) / 1e12 if tms > 0 else 0.0
         roof = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                "traffic": None, "kernel": "gemm_tcgen05_kernel", "launches_timed": len(tc),
+                "traffic": None, "kernel": "gemm_tcgen05_kernel", "launches_timed": len(records),
+                "avg_launch_us": tms * 1e3 / len(records),
+                "method": "all tcgen05 GEMM launches of one train step replayed back to back in a CUDA graph, CUDA events",
                 "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)"
-                if peaks else "fallback 1400.2 (sustained)",
-                "gemm_share_of_step": (tms / 2) / (ms / args.steps) if ms > 0 else None}
-    else:
-        # other ranks run the same two extra steps so collectives stay matched
-        for i in range(2):
-            eager_step(i)
-        torch.cuda.synchronize()
+                if peaks else "fallback 1400 (sustained, B200_PROFILING.md)",
+                "gemm_share_of_step": tms / (ms / args.steps) if ms > 0 else None}
+        del graph
+    records.clear()
 
     if rank == 0:
         train_flops = flops_per_image(spec, train=True)

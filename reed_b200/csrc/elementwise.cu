@@ -12,57 +12,127 @@ namespace reed {
 constexpr int kRowWarps = 4;   // warps per CTA in the row kernels
 
 // ---------------------------------------------------------------------------------------------
-// out[m,:] = LN(x[m,:]) * (1 + scale[g,:]) + shift[g,:],  g = m / rows_per_group
+// Row streaming: the HBM-bound row kernels keep `kRowStages` whole rows per CTA in flight with 1-D TMA bulk copies
+// (cp.async.bulk global -> shared, completion on an mbarrier), so the bytes in flight are bounded by shared memory
+// (tens of KB per CTA) instead of by registers; threads then pick their float4 column groups out of shared memory.
 // ---------------------------------------------------------------------------------------------
+constexpr int kRowStages = 4;
+
+__device__ __forceinline__ uint32_t row_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void row_bar_init(uint64_t* bar) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(row_smem_u32(bar)));
+}
+__device__ __forceinline__ void row_bar_expect(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(row_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void row_bar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = row_smem_u32(bar);
+  uint32_t done = 0;
+  while (!done) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+  }
+}
+// bytes: multiple of 16; src, dst 16-byte aligned
+__device__ __forceinline__ void row_bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(row_smem_u32(dst)), "l"(src), "r"(bytes), "r"(row_smem_u32(bar))
+               : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------
+// out[m,:] = LN(x[m,:]) * (1 + scale[g,:]) + shift[g,:],  g = m / rows_per_group
+// One warp per row at a time; each warp streams its rows (row, row + total_warps, ...) through a private ring of
+// kRowStages shared-memory row buffers filled by bulk copies it issues itself.
+// ---------------------------------------------------------------------------------------------
+constexpr int kLnWarps = 8;
+constexpr int kLnStages = 2;
+
 template <typename TA, int MAXV>
-__global__ void __launch_bounds__(kRowWarps * 32) ln_modulate_fwd_kernel(
+__global__ void __launch_bounds__(kLnWarps * 32) ln_modulate_fwd_kernel(
     const float* __restrict__ x, const float* __restrict__ shift, const float* __restrict__ scale, int64_t ld_mod,
     int rows_per_group, TA* __restrict__ out, float* __restrict__ mean_out, float* __restrict__ rstd_out, int M, int D,
     float eps) {
-  const int lane = threadIdx.x & 31;
-  const int row = blockIdx.x * kRowWarps + (threadIdx.x >> 5);
-  if (row >= M) return;
-  const float* xr = x + (int64_t)row * D;
-  F4 c[MAXV];
-  float s = 0.f;
+  extern __shared__ __align__(128) uint8_t ln_smem[];
+  __shared__ uint64_t bars[kLnWarps][kLnStages];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int total_warps = gridDim.x * kLnWarps;
+  const int first = blockIdx.x * kLnWarps + warp;
+  float* ring = reinterpret_cast<float*>(ln_smem) + (size_t)warp * kLnStages * D;
+  const uint32_t row_bytes = (uint32_t)D * 4u;
+  if (lane == 0) {
 #pragma unroll
-  for (int i = 0; i < MAXV; ++i) {
-    int col = (i * 32 + lane) * 4;
-    if (col < D) {
-      c[i] = load4(xr + col);
-      s += (c[i].v[0] + c[i].v[1]) + (c[i].v[2] + c[i].v[3]);
-    }
-  }
-  const float mean = warp_sum(s) / D;
-  float q = 0.f;
+    for (int s = 0; s < kLnStages; ++s) row_bar_init(&bars[warp][s]);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 #pragma unroll
-  for (int i = 0; i < MAXV; ++i) {
-    int col = (i * 32 + lane) * 4;
-    if (col < D) {
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        float d = c[i].v[j] - mean;
-        q += d * d;
+    for (int s = 0; s < kLnStages; ++s) {
+      const int row = first + s * total_warps;
+      if (row < M) {
+        row_bar_expect(&bars[warp][s], row_bytes);
+        row_bulk_load(ring + (size_t)s * D, x + (int64_t)row * D, row_bytes, &bars[warp][s]);
       }
     }
   }
-  const float rstd = rsqrtf(warp_sum(q) / D + eps);
-  if (lane == 0) {
-    mean_out[row] = mean;
-    rstd_out[row] = rstd;
-  }
-  const int g = row / rows_per_group;
-  const float* sh = shift + (int64_t)g * ld_mod;
-  const float* sc = scale + (int64_t)g * ld_mod;
-  TA* o = out + (int64_t)row * D;
+  __syncwarp();
+  int it = 0;
+  for (int row = first; row < M; row += total_warps, ++it) {
+    const int slot = it % kLnStages;
+    row_bar_wait(&bars[warp][slot], (uint32_t)(it / kLnStages) & 1u);
+    const float* xr = ring + (size_t)slot * D;
+    F4 c[MAXV];
+    float s = 0.f;
 #pragma unroll
-  for (int i = 0; i < MAXV; ++i) {
-    int col = (i * 32 + lane) * 4;
-    if (col < D) {
-      F4 a = load4(sh + col), b = load4(sc + col), r;
+    for (int i = 0; i < MAXV; ++i) {
+      int col = (i * 32 + lane) * 4;
+      if (col < D) {
+        c[i] = load4(xr + col);
+        s += (c[i].v[0] + c[i].v[1]) + (c[i].v[2] + c[i].v[3]);
+      }
+    }
+    __syncwarp();          // every lane has its values in registers: the slot can be refilled
+    if (lane == 0) {
+      const int nrow = row + kLnStages * total_warps;
+      if (nrow < M) {
+        row_bar_expect(&bars[warp][slot], row_bytes);
+        row_bulk_load(ring + (size_t)slot * D, x + (int64_t)nrow * D, row_bytes, &bars[warp][slot]);
+      }
+    }
+    const float mean = warp_sum(s) / D;
+    float q = 0.f;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) r.v[j] = (c[i].v[j] - mean) * rstd * (1.f + b.v[j]) + a.v[j];
-      store4(o + col, r);
+    for (int i = 0; i < MAXV; ++i) {
+      int col = (i * 32 + lane) * 4;
+      if (col < D) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float d = c[i].v[j] - mean;
+          q += d * d;
+        }
+      }
+    }
+    const float rstd = rsqrtf(warp_sum(q) / D + eps);
+    if (lane == 0) {
+      mean_out[row] = mean;
+      rstd_out[row] = rstd;
+    }
+    const int g = row / rows_per_group;
+    const float* sh = shift + (int64_t)g * ld_mod;
+    const float* sc = scale + (int64_t)g * ld_mod;
+    TA* o = out + (int64_t)row * D;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      int col = (i * 32 + lane) * 4;
+      if (col < D) {
+        F4 a = load4(sh + col), b = load4(sc + col), r;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) r.v[j] = (c[i].v[j] - mean) * rstd * (1.f + b.v[j]) + a.v[j];
+        store4(o + col, r);
+      }
     }
   }
 }
@@ -107,47 +177,50 @@ __device__ __forceinline__ void red_add_v4(float* p, const F4& f) {
 
 constexpr int kRowMaxThreads = 384;
 
-template <typename TA, int V, bool LN, bool GATE>
-struct RowRegs {           // one row's operands for one thread (V float4 column groups)
-  F4 d[LN ? V : 1], xv[LN ? V : 1], gin[V], yv[GATE ? V : 1];
-  float mean, rstd;
-};
-
-template <typename TA, int V, bool LN, bool GATE>
-__device__ __forceinline__ void row_load(RowRegs<TA, V, LN, GATE>& r, const RowBwdParams& p, int row, const int (&col)[V],
-                                         const bool (&ok)[V]) {
-  const int64_t base = (int64_t)row * p.D;
-  const TA* __restrict__ dout = reinterpret_cast<const TA*>(p.dout);
-  const TA* __restrict__ y = reinterpret_cast<const TA*>(p.y);
-#pragma unroll
-  for (int i = 0; i < V; ++i) {
-    r.gin[i] = F4{{0, 0, 0, 0}};
-    if (ok[i]) {
-      if constexpr (LN) {
-        r.d[i] = load4(dout + base + col[i]);
-        r.xv[i] = load4(p.x + base + col[i]);
-      }
-      if (!LN || p.dres != nullptr) r.gin[i] = load4(p.dres + base + col[i]);
-      if constexpr (GATE) r.yv[i] = load4(y + base + col[i]);
-    }
-  }
-  if constexpr (LN) {
-    r.mean = p.mean[row];
-    r.rstd = p.rstd[row];
-  }
+// bytes of one row's operands in the shared-memory ring of row_bwd_kernel
+template <typename TA, bool LN, bool GATE>
+__host__ __device__ inline int row_slot_bytes(int D, bool has_res) {
+  return (LN ? D * (int)sizeof(TA) + D * 4 : 0) + (has_res ? D * 4 : 0) + (GATE ? D * (int)sizeof(TA) : 0);
 }
 
 template <typename TA, int V, bool LN, bool GATE>
 __global__ void __launch_bounds__(kRowMaxThreads) row_bwd_kernel(const RowBwdParams p) {
+  extern __shared__ __align__(128) uint8_t row_smem[];
+  __shared__ uint64_t full[kRowStages];
   __shared__ float2 red[2][kRowMaxThreads / 32];
   const int NT = blockDim.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = NT >> 5;
   const int D = p.D;
-  const int chunks_per_group = (p.rows_per_group + p.rows_per_cta - 1) / p.rows_per_cta;
-  const int g = blockIdx.x / chunks_per_group;
-  const int r0 = g * p.rows_per_group + (blockIdx.x % chunks_per_group) * p.rows_per_cta;
-  const int r1 = min(r0 + p.rows_per_cta, (g + 1) * p.rows_per_group);
+  const int r0 = blockIdx.x * p.rows_per_cta;
+  const int r1 = min(r0 + p.rows_per_cta, p.M);
   TA* __restrict__ dy = reinterpret_cast<TA*>(p.dy);
   const float inv_d = 1.f / D;
+  const bool has_res = !LN || p.dres != nullptr;
+  // slot layout: [dout TA | x f32] (LN) [dres f32] (has_res) [y TA] (GATE)
+  const int o_x = LN ? D * (int)sizeof(TA) : 0;
+  const int o_r = o_x + (LN ? D * 4 : 0);
+  const int o_y = o_r + (has_res ? D * 4 : 0);
+  const int slot_bytes = o_y + (GATE ? D * (int)sizeof(TA) : 0);
+
+  auto issue = [&](int row, int slot) {       // thread 0: all operands of one row -> ring slot
+    uint8_t* dst = row_smem + (size_t)slot * slot_bytes;
+    const int64_t base = (int64_t)row * D;
+    row_bar_expect(&full[slot], (uint32_t)slot_bytes);
+    if constexpr (LN) {
+      row_bulk_load(dst, reinterpret_cast<const TA*>(p.dout) + base, (uint32_t)(D * sizeof(TA)), &full[slot]);
+      row_bulk_load(dst + o_x, p.x + base, (uint32_t)D * 4u, &full[slot]);
+    }
+    if (has_res) row_bulk_load(dst + o_r, p.dres + base, (uint32_t)D * 4u, &full[slot]);
+    if constexpr (GATE) row_bulk_load(dst + o_y, reinterpret_cast<const TA*>(p.y) + base, (uint32_t)(D * sizeof(TA)), &full[slot]);
+  };
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < kRowStages; ++s) row_bar_init(&full[s]);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+#pragma unroll
+    for (int s = 0; s < kRowStages; ++s)
+      if (r0 + s < r1) issue(r0 + s, s);
+  }
+  __syncthreads();
 
   int col[V];
   bool ok[V];
@@ -157,46 +230,93 @@ __global__ void __launch_bounds__(kRowMaxThreads) row_bwd_kernel(const RowBwdPar
   for (int i = 0; i < V; ++i) {
     col[i] = (tid + i * NT) * 4;
     ok[i] = col[i] < D;
-    if constexpr (LN) {
-      a_sh[i] = F4{{0, 0, 0, 0}};
-      a_sc[i] = F4{{0, 0, 0, 0}};
-      one_plus[i] = F4{{1, 1, 1, 1}};
-      if (ok[i]) {
-        const F4 s = load4(p.scale + (int64_t)g * p.ld_mod + col[i]);
+  }
+  auto load_group = [&](int g) {              // per-group modulation vectors; column partial sums restart
 #pragma unroll
-        for (int j = 0; j < 4; ++j) one_plus[i].v[j] = 1.f + s.v[j];
+    for (int i = 0; i < V; ++i) {
+      if constexpr (LN) {
+        a_sh[i] = F4{{0, 0, 0, 0}};
+        a_sc[i] = F4{{0, 0, 0, 0}};
+        one_plus[i] = F4{{1, 1, 1, 1}};
+        if (ok[i]) {
+          const F4 s = load4(p.scale + (int64_t)g * p.ld_mod + col[i]);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) one_plus[i].v[j] = 1.f + s.v[j];
+        }
+      }
+      if constexpr (GATE) {
+        a_g[i] = F4{{0, 0, 0, 0}};
+        a_b[i] = F4{{0, 0, 0, 0}};
+        gt[i] = F4{{0, 0, 0, 0}};
+        if (ok[i]) gt[i] = load4(p.gate + (int64_t)g * p.ld_mod + col[i]);
       }
     }
-    if constexpr (GATE) {
-      a_g[i] = F4{{0, 0, 0, 0}};
-      a_b[i] = F4{{0, 0, 0, 0}};
-      gt[i] = F4{{0, 0, 0, 0}};
-      if (ok[i]) gt[i] = load4(p.gate + (int64_t)g * p.ld_mod + col[i]);
+  };
+  auto flush_group = [&](int g) {
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      if (ok[i]) {
+        const int64_t off = (int64_t)g * p.ld_mod + col[i];
+        if constexpr (LN) {
+          red_add_v4(p.dshift + off, a_sh[i]);
+          red_add_v4(p.dscale + off, a_sc[i]);
+        }
+        if constexpr (GATE) {
+          red_add_v4(p.dgate + off, a_g[i]);
+          if (p.dbias != nullptr) red_add_v4(p.dbias + col[i], a_b[i]);
+        }
+      }
     }
-  }
+  };
 
-  // software pipeline over rows: the loads of row r+1 are in flight while row r is reduced and stored
-  RowRegs<TA, V, LN, GATE> cur, nxt;
-  row_load<TA, V, LN, GATE>(cur, p, r0, col, ok);
-  int buf = 0;
-  for (int row = r0; row < r1; ++row) {
-    if (row + 1 < r1) row_load<TA, V, LN, GATE>(nxt, p, row + 1, col, ok);
-    const int64_t base = (int64_t)row * D;
+  int g = r0 / p.rows_per_group;
+  load_group(g);
+  float mean_n = 0.f, rstd_n = 0.f;
+  if constexpr (LN) {
+    if (r0 < r1) { mean_n = p.mean[r0]; rstd_n = p.rstd[r0]; }
+  }
+  int buf = 0, it = 0;
+  for (int row = r0; row < r1; ++row, ++it) {
+    const int gr = row / p.rows_per_group;
+    if (gr != g) {                            // the CTA's row range crosses into the next sample
+      flush_group(g);
+      g = gr;
+      load_group(g);
+    }
+    const float mean = mean_n, rstd = rstd_n;
     if constexpr (LN) {
-      const float mean = cur.mean, rstd = cur.rstd;
-      float s1 = 0.f, s2 = 0.f;
+      if (row + 1 < r1) { mean_n = p.mean[row + 1]; rstd_n = p.rstd[row + 1]; }
+    }
+    const int slot = it % kRowStages;
+    row_bar_wait(&full[slot], (uint32_t)(it / kRowStages) & 1u);
+    const uint8_t* src = row_smem + (size_t)slot * slot_bytes;
+    F4 d[LN ? V : 1], xv[LN ? V : 1], gin[V], yv[GATE ? V : 1];
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      gin[i] = F4{{0, 0, 0, 0}};
+      if (ok[i]) {
+        if constexpr (LN) {
+          d[i] = load4(reinterpret_cast<const TA*>(src) + col[i]);
+          xv[i] = load4(reinterpret_cast<const float*>(src + o_x) + col[i]);
+        }
+        if (has_res) gin[i] = load4(reinterpret_cast<const float*>(src + o_r) + col[i]);
+        if constexpr (GATE) yv[i] = load4(reinterpret_cast<const TA*>(src + o_y) + col[i]);
+      }
+    }
+    float s1 = 0.f, s2 = 0.f;
+    if constexpr (LN) {
 #pragma unroll
       for (int i = 0; i < V; ++i) {
         if (ok[i]) {
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            const float h = (cur.xv[i].v[j] - mean) * rstd;
-            const float dv = cur.d[i].v[j];
-            cur.xv[i].v[j] = h;
+            const float h = (xv[i].v[j] - mean) * rstd;
+            const float dv = d[i].v[j];
+            xv[i].v[j] = h;
             a_sh[i].v[j] += dv;
             a_sc[i].v[j] += dv * h;
             const float e = dv * one_plus[i].v[j];
-            cur.d[i].v[j] = e;
+            d[i].v[j] = e;
             s1 += e;
             s2 += e * h;
           }
@@ -204,25 +324,29 @@ __global__ void __launch_bounds__(kRowMaxThreads) row_bwd_kernel(const RowBwdPar
       }
       s1 = warp_sum(s1);
       s2 = warp_sum(s2);
-      if (nwarps > 1) {
-        if (lane == 0) red[buf][warp] = make_float2(s1, s2);
-        __syncthreads();
-        s1 = 0.f;
-        s2 = 0.f;
-        for (int w = 0; w < nwarps; ++w) {
-          const float2 t = red[buf][w];
-          s1 += t.x;
-          s2 += t.y;
-        }
-        buf ^= 1;    // the next row uses the other slot: one barrier per row is enough
+      if (lane == 0) red[buf][warp] = make_float2(s1, s2);
+    }
+    // one barrier per row: every thread has copied its operands out of the slot (it can be refilled) and, for LN,
+    // the per-warp partial sums are visible
+    __syncthreads();
+    if (tid == 0 && row + kRowStages < r1) issue(row + kRowStages, slot);
+    const int64_t base = (int64_t)row * D;
+    if constexpr (LN) {
+      s1 = 0.f;
+      s2 = 0.f;
+      for (int w = 0; w < nwarps; ++w) {
+        const float2 t = red[buf][w];
+        s1 += t.x;
+        s2 += t.y;
       }
+      buf ^= 1;    // the next row uses the other slot of `red`
       const float c1 = s1 * inv_d, c2 = s2 * inv_d;
 #pragma unroll
       for (int i = 0; i < V; ++i) {
         if (ok[i]) {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) cur.gin[i].v[j] += rstd * (cur.d[i].v[j] - c1 - cur.xv[i].v[j] * c2);
-          store4(p.dx + base + col[i], cur.gin[i]);
+          for (int j = 0; j < 4; ++j) gin[i].v[j] += rstd * (d[i].v[j] - c1 - xv[i].v[j] * c2);
+          store4(p.dx + base + col[i], gin[i]);
         }
       }
     }
@@ -233,30 +357,16 @@ __global__ void __launch_bounds__(kRowMaxThreads) row_bwd_kernel(const RowBwdPar
           F4 o;
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            a_g[i].v[j] += cur.gin[i].v[j] * cur.yv[i].v[j];
-            o.v[j] = to_f(from_f<TA>(cur.gin[i].v[j] * gt[i].v[j]));
+            a_g[i].v[j] += gin[i].v[j] * yv[i].v[j];
+            o.v[j] = to_f(from_f<TA>(gin[i].v[j] * gt[i].v[j]));
             a_b[i].v[j] += o.v[j];
           }
           store4(dy + base + col[i], o);
         }
       }
     }
-    cur = nxt;
   }
-#pragma unroll
-  for (int i = 0; i < V; ++i) {
-    if (ok[i]) {
-      const int64_t off = (int64_t)g * p.ld_mod + col[i];
-      if constexpr (LN) {
-        red_add_v4(p.dshift + off, a_sh[i]);
-        red_add_v4(p.dscale + off, a_sc[i]);
-      }
-      if constexpr (GATE) {
-        red_add_v4(p.dgate + off, a_g[i]);
-        if (p.dbias != nullptr) red_add_v4(p.dbias + col[i], a_b[i]);
-      }
-    }
-  }
+  if (r0 < r1) flush_group(g);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -376,24 +486,71 @@ static inline int flat_grid(int64_t n4) {
   return (int)(b < cap ? (b < 1 ? 1 : b) : cap);
 }
 
-template <typename TA>
-static int ln_fwd_dispatch(const float* x, const float* shift, const float* scale, int64_t ld_mod, int rpg, void* out,
-                           float* mean, float* rstd, int M, int D, float eps, cudaStream_t st) {
-  dim3 grid(ceil_div(M, kRowWarps)), block(kRowWarps * 32);
-  int nv = ceil_div(D, 128);
-#define LN_FWD(V) ln_modulate_fwd_kernel<TA, V><<<grid, block, 0, st>>>(x, shift, scale, ld_mod, rpg, (TA*)out, mean, rstd, M, D, eps)
-  if (nv <= 4) LN_FWD(4); else if (nv <= 8) LN_FWD(8); else if (nv <= 12) LN_FWD(12); else LN_FWD(16);
-#undef LN_FWD
+static int row_sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = kNumSMs;
+  }
+  return n;
+}
+
+template <typename TA, int V>
+static int ln_fwd_launch(const float* x, const float* shift, const float* scale, int64_t ld_mod, int rpg, void* out,
+                         float* mean, float* rstd, int M, int D, float eps, cudaStream_t st) {
+  auto kernel = ln_modulate_fwd_kernel<TA, V>;
+  const int smem = kLnWarps * kLnStages * D * 4;
+  static int configured = 0;
+  if (configured < smem) {
+    REED_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = smem;
+  }
+  // persistent: as many CTAs as fit (shared memory bound), every warp strides over the rows
+  int per_sm = (226 * 1024) / (smem + 1024);
+  if (per_sm > 8) per_sm = 8;
+  if (per_sm < 1) per_sm = 1;
+  int grid = row_sm_count() * per_sm;
+  const int need = ceil_div(M, kLnWarps);
+  if (grid > need) grid = need;
+  kernel<<<grid, kLnWarps * 32, smem, st>>>(x, shift, scale, ld_mod, rpg, (TA*)out, mean, rstd, M, D, eps);
   REED_LAUNCH_CHECK();
   return 0;
 }
 
-static int rows_per_cta_for(int M, int rpg) {
+template <typename TA>
+static int ln_fwd_dispatch(const float* x, const float* shift, const float* scale, int64_t ld_mod, int rpg, void* out,
+                           float* mean, float* rstd, int M, int D, float eps, cudaStream_t st) {
+  int nv = ceil_div(D, 128);
+#define LN_FWD(V) return ln_fwd_launch<TA, V>(x, shift, scale, ld_mod, rpg, out, mean, rstd, M, D, eps, st)
+  if (nv <= 4) LN_FWD(4); else if (nv <= 9) LN_FWD(9); else if (nv <= 12) LN_FWD(12); else LN_FWD(16);
+#undef LN_FWD
+}
+
+template <typename TA, int V, bool LN, bool GATE>
+static int row_bwd_launch(RowBwdParams p, int threads, cudaStream_t st) {
+  auto kernel = row_bwd_kernel<TA, V, LN, GATE>;
+  const bool has_res = !LN || p.dres != nullptr;
+  const int smem = kRowStages * row_slot_bytes<TA, LN, GATE>(p.D, has_res);
+  static int configured = 0;
+  if (configured < smem) {
+    REED_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = smem;
+  }
+  // one balanced wave: as many CTAs as are resident at once (shared-memory / thread bound), equal row ranges that
+  // may cross sample boundaries (the kernel flushes its column partials when the group changes)
   static const int forced = getenv("REED_ROWS_PER_CTA") ? atoi(getenv("REED_ROWS_PER_CTA")) : 0;
-  int r = forced > 0 ? forced : 8;
-  // keep at least ~4 CTAs per SM in flight; never straddle a group
-  while (!forced && r > 1 && (int64_t)M / r < 4 * kNumSMs) r >>= 1;
-  return r < rpg ? r : rpg;
+  int per_sm = (220 * 1024) / (smem + 1024);
+  const int by_threads = 2048 / threads;
+  if (per_sm > by_threads) per_sm = by_threads;
+  if (per_sm > 4) per_sm = 4;
+  if (per_sm < 1) per_sm = 1;
+  int rows = forced > 0 ? forced : ceil_div(p.M, row_sm_count() * per_sm);
+  if (rows < 1) rows = 1;
+  p.rows_per_cta = rows;
+  kernel<<<ceil_div(p.M, rows), threads, smem, st>>>(p);
+  REED_LAUNCH_CHECK();
+  return 0;
 }
 
 template <typename TA, bool LN, bool GATE>
@@ -401,14 +558,8 @@ static int row_bwd_dispatch(RowBwdParams p, cudaStream_t st) {
   const int D = p.D;
   const int V = ceil_div(D, 4 * kRowMaxThreads);            // float4 column groups per thread (1 up to D = 1536)
   const int threads = ceil_div(ceil_div(D / 4, V), 32) * 32;
-  p.rows_per_cta = rows_per_cta_for(p.M, p.rows_per_group);
-  const int chunks = ceil_div(p.rows_per_group, p.rows_per_cta);
-  dim3 grid((p.M / p.rows_per_group) * chunks), block(threads);
-#define RB(VV) row_bwd_kernel<TA, VV, LN, GATE><<<grid, block, 0, st>>>(p)
-  if (V == 1) RB(1); else RB(2);
-#undef RB
-  REED_LAUNCH_CHECK();
-  return 0;
+  if (V == 1) return row_bwd_launch<TA, 1, LN, GATE>(p, threads, st);
+  return row_bwd_launch<TA, 2, LN, GATE>(p, threads, st);
 }
 
 }  // namespace reed
@@ -416,7 +567,7 @@ static int row_bwd_dispatch(RowBwdParams p, cudaStream_t st) {
 using namespace reed;
 
 #define ROW_ARGS_OK(M, D, rpg)                                                                   \
-  REED_REQUIRE((D) % 4 == 0 && (D) <= 2048, "row kernels need D %% 4 == 0 and D <= 2048, got %d", (int)(D)); \
+  REED_REQUIRE((D) % 8 == 0 && (D) <= 2048, "row kernels need D %% 8 == 0 and D <= 2048, got %d", (int)(D)); \
   REED_REQUIRE((rpg) > 0 && (M) % (rpg) == 0, "M=%d not a multiple of rows_per_group=%d", (int)(M), (int)(rpg))
 
 extern "C" int reed_ln_modulate_fwd(const void* x, const void* shift, const void* scale, int64_t ld_mod,

@@ -44,7 +44,12 @@ struct GemmCfg {
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kStagingBytes = kEpiWarps * 32 * kStagePitch * 4;
   static constexpr int kBudget = 227 * 1024 - 1024 /*align slack*/ - kStagingBytes - 256 /*barriers*/;
-  static constexpr int kStages = (kBudget / kStageBytes) > 8 ? 8 : (kBudget / kStageBytes);
+  static constexpr int kStagesFit = (kBudget / kStageBytes) > 8 ? 8 : (kBudget / kStageBytes);
+#ifdef REED_GEMM_MAX_STAGES
+  static constexpr int kStages = kStagesFit > REED_GEMM_MAX_STAGES ? REED_GEMM_MAX_STAGES : kStagesFit;
+#else
+  static constexpr int kStages = kStagesFit;
+#endif
   static constexpr int kSmemBytes = 1024 + kStages * kStageBytes + kStagingBytes + 256;
   static constexpr int kTmemCols = 2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512);
 };
