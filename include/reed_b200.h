@@ -54,6 +54,15 @@ int reed_attn_fwd(int act_dtype, const void* qkv, void* o, void* lse, int B, int
 int reed_attn_bwd(int act_dtype, const void* qkv, const void* o, const void* d_o, const void* lse, void* dqkv,
                   void* delta, int B, int T, int H, int hd, int backend, void* stream);
 
+/* Optional q/k LayerNorm of timm Attention(qk_norm=True) (models/sit.py:114-116; nn.LayerNorm(head_dim), eps 1e-5),
+ * applied per (token, head) to the q and k thirds of the packed qkv [rows, 3, H, hd]; v is copied through.
+ *   fwd: out (act dtype, same layout), stats fp32 [rows, H, 2, 2] = (mean, rstd) of q and k (saved for backward).
+ *   bwd: dqkv (w.r.t. the raw qkv) from dout (w.r.t. the normalised one); dwq/dbq/dwk/dbk fp32 [hd] accumulated into. */
+int reed_qk_norm_fwd(const void* qkv, int act_dtype, const void* wq, const void* bq, const void* wk, const void* bk,
+                     void* out, void* stats, int64_t rows, int H, int hd, float eps, void* stream);
+int reed_qk_norm_bwd(const void* dout, int act_dtype, const void* qkv, const void* stats, const void* wq, const void* wk,
+                     void* dqkv, void* dwq, void* dbq, void* dwk, void* dbk, int64_t rows, int H, int hd, void* stream);
+
 /* out = LayerNorm(x; no affine, eps) * (1 + scale[g]) + shift[g], g = row / rows_per_group.
  * Replaces norm1/norm2/norm_final + modulate (models/sit.py:26-27,113,119,134-135,146,155).
  *   x fp32 [M,D]; shift/scale fp32 rows of pitch ld_mod; out act dtype [M,D]; mean/rstd fp32 [M] (saved). */

@@ -562,6 +562,134 @@ static int row_bwd_dispatch(RowBwdParams p, cudaStream_t st) {
   return row_bwd_launch<TA, 2, LN, GATE>(p, threads, st);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Optional per-head LayerNorm of q and k (timm Attention(qk_norm=True): nn.LayerNorm(head_dim), affine, eps 1e-5),
+// applied to the packed qkv [rows, 3, H, hd]; v is copied through.  One warp per (row, head) unit of one of q/k/v
+// (blockIdx.y), element i of the unit in lane i % 32.  Backward keeps dweight/dbias partials in registers across
+// the warp's units and flushes them with atomics.
+// ---------------------------------------------------------------------------------------------
+template <typename TA>
+__global__ void __launch_bounds__(256) qk_norm_fwd_kernel(const TA* __restrict__ qkv, const float* __restrict__ wq,
+                                                           const float* __restrict__ bq, const float* __restrict__ wk,
+                                                           const float* __restrict__ bk, TA* __restrict__ out,
+                                                           float* __restrict__ stats, int64_t rows, int H, int hd, float eps) {
+  const int lane = threadIdx.x & 31;
+  const int which = blockIdx.y;
+  const int64_t units = rows * H;
+  const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  const float* w = which == 0 ? wq : wk;
+  const float* b = which == 0 ? bq : bk;
+  for (int64_t u = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); u < units; u += warps) {
+    const int64_t row = u / H;
+    const int h = (int)(u - row * H);
+    const int64_t base = (row * 3 + which) * (int64_t)H * hd + (int64_t)h * hd;
+    float v[4];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int c = lane + 32 * i;
+      v[i] = c < hd ? to_f(qkv[base + c]) : 0.f;
+      s += v[i];
+    }
+    if (which == 2) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int c = lane + 32 * i;
+        if (c < hd) out[base + c] = from_f<TA>(v[i]);
+      }
+      continue;
+    }
+    const float mean = warp_sum(s) / hd;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int c = lane + 32 * i;
+      if (c < hd) q += (v[i] - mean) * (v[i] - mean);
+    }
+    const float rstd = rsqrtf(warp_sum(q) / hd + eps);
+    if (lane == 0) {
+      stats[(u * 2 + which) * 2] = mean;
+      stats[(u * 2 + which) * 2 + 1] = rstd;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int c = lane + 32 * i;
+      if (c < hd) out[base + c] = from_f<TA>((v[i] - mean) * rstd * w[c] + b[c]);
+    }
+  }
+}
+
+template <typename TA>
+__global__ void __launch_bounds__(256) qk_norm_bwd_kernel(const TA* __restrict__ dout, const TA* __restrict__ qkv,
+                                                           const float* __restrict__ stats, const float* __restrict__ wq,
+                                                           const float* __restrict__ wk, TA* __restrict__ dqkv,
+                                                           float* __restrict__ dwq, float* __restrict__ dbq,
+                                                           float* __restrict__ dwk, float* __restrict__ dbk, int64_t rows,
+                                                           int H, int hd) {
+  const int lane = threadIdx.x & 31;
+  const int which = blockIdx.y;
+  const int64_t units = rows * H;
+  const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  const float* w = which == 0 ? wq : wk;
+  float wv[4], dw[4], db[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int c = lane + 32 * i;
+    wv[i] = (which < 2 && c < hd) ? w[c] : 0.f;
+    dw[i] = 0.f;
+    db[i] = 0.f;
+  }
+  for (int64_t u = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); u < units; u += warps) {
+    const int64_t row = u / H;
+    const int h = (int)(u - row * H);
+    const int64_t base = (row * 3 + which) * (int64_t)H * hd + (int64_t)h * hd;
+    float dy[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int c = lane + 32 * i;
+      dy[i] = c < hd ? to_f(dout[base + c]) : 0.f;
+    }
+    if (which == 2) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int c = lane + 32 * i;
+        if (c < hd) dqkv[base + c] = from_f<TA>(dy[i]);
+      }
+      continue;
+    }
+    const float mean = stats[(u * 2 + which) * 2], rstd = stats[(u * 2 + which) * 2 + 1];
+    float xh[4], g[4], s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int c = lane + 32 * i;
+      xh[i] = c < hd ? (to_f(qkv[base + c]) - mean) * rstd : 0.f;
+      g[i] = dy[i] * wv[i];
+      s1 += g[i];
+      s2 += g[i] * xh[i];
+      dw[i] += dy[i] * xh[i];
+      db[i] += dy[i];
+    }
+    const float c1 = warp_sum(s1) / hd, c2 = warp_sum(s2) / hd;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int c = lane + 32 * i;
+      if (c < hd) dqkv[base + c] = from_f<TA>(rstd * (g[i] - c1 - xh[i] * c2));
+    }
+  }
+  if (which < 2) {
+    float* dwp = which == 0 ? dwq : dwk;
+    float* dbp = which == 0 ? dbq : dbk;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int c = lane + 32 * i;
+      if (c < hd) {
+        atomicAdd(dwp + c, dw[i]);
+        atomicAdd(dbp + c, db[i]);
+      }
+    }
+  }
+}
+
 }  // namespace reed
 
 using namespace reed;
@@ -709,6 +837,48 @@ extern "C" int reed_add_f32(const void* a, const void* b, void* out, int64_t n, 
   REED_REQUIRE(n % 4 == 0, "add needs n %% 4 == 0");
   if (n == 0) return 0;
   add_kernel<<<flat_grid(n / 4), 256, 0, (cudaStream_t)stream>>>((const float*)a, (const float*)b, (float*)out, n / 4);
+  REED_LAUNCH_CHECK();
+  return 0;
+}
+
+// q/k LayerNorm over head_dim of the packed qkv (timm Attention q_norm / k_norm, affine, eps 1e-5); stats [rows,H,2,2]
+extern "C" int reed_qk_norm_fwd(const void* qkv, int act_dtype, const void* wq, const void* bq, const void* wk,
+                                const void* bk, void* out, void* stats, int64_t rows, int H, int hd, float eps,
+                                void* stream) {
+  REED_REQUIRE(hd >= 1 && hd <= 128, "qk_norm: head_dim %d unsupported (1..128)", hd);
+  if (rows == 0) return 0;
+  int64_t blocks = (rows * H + 7) / 8;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  dim3 grid((unsigned)blocks, 3);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (act_dtype == kBF16)
+    qk_norm_fwd_kernel<bf16><<<grid, 256, 0, st>>>((const bf16*)qkv, (const float*)wq, (const float*)bq, (const float*)wk,
+                                                    (const float*)bk, (bf16*)out, (float*)stats, rows, H, hd, eps);
+  else
+    qk_norm_fwd_kernel<float><<<grid, 256, 0, st>>>((const float*)qkv, (const float*)wq, (const float*)bq, (const float*)wk,
+                                                     (const float*)bk, (float*)out, (float*)stats, rows, H, hd, eps);
+  REED_LAUNCH_CHECK();
+  return 0;
+}
+
+// dqkv (raw) from the gradient w.r.t. the normalised qkv; dwq/dbq/dwk/dbk fp32 [hd] are accumulated into
+extern "C" int reed_qk_norm_bwd(const void* dout, int act_dtype, const void* qkv, const void* stats, const void* wq,
+                                const void* wk, void* dqkv, void* dwq, void* dbq, void* dwk, void* dbk, int64_t rows,
+                                int H, int hd, void* stream) {
+  REED_REQUIRE(hd >= 1 && hd <= 128, "qk_norm: head_dim %d unsupported (1..128)", hd);
+  if (rows == 0) return 0;
+  int64_t blocks = (rows * H + 7) / 8;
+  if (blocks > 148 * 4) blocks = 148 * 4;
+  dim3 grid((unsigned)blocks, 3);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (act_dtype == kBF16)
+    qk_norm_bwd_kernel<bf16><<<grid, 256, 0, st>>>((const bf16*)dout, (const bf16*)qkv, (const float*)stats,
+                                                    (const float*)wq, (const float*)wk, (bf16*)dqkv, (float*)dwq,
+                                                    (float*)dbq, (float*)dwk, (float*)dbk, rows, H, hd);
+  else
+    qk_norm_bwd_kernel<float><<<grid, 256, 0, st>>>((const float*)dout, (const float*)qkv, (const float*)stats,
+                                                     (const float*)wq, (const float*)wk, (float*)dqkv, (float*)dwq,
+                                                     (float*)dbq, (float*)dwk, (float*)dbk, rows, H, hd);
   REED_LAUNCH_CHECK();
   return 0;
 }

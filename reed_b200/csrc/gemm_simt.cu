@@ -79,9 +79,80 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const TA* __restrict__ A
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Weight gradient over a handful of rows: D[N, K] (+)= sum_b dy[b, N] * x[b, K], b < 64 (the adaLN / embedder linears,
+// whose contraction is the batch).  An outer-product stream: 2 small operand tiles in shared memory, every thread
+// owns a 4 x 4 output block, rows written as coalesced float4 - bounded by the HBM write of N*K floats.
+// ------------------------------------------------------------------------------------------------
+constexpr int kOwN = 32, kOwK = 128;
+
+template <typename TA>
+__global__ void __launch_bounds__(256) outer_wgrad_kernel(const TA* __restrict__ dy, int64_t ld_dy, const TA* __restrict__ x,
+                                                           int64_t ld_x, float* __restrict__ D, int64_t ldd, int N, int K,
+                                                           int B, int accumulate) {
+  __shared__ float sdy[64][kOwN];
+  __shared__ float sx[64][kOwK];
+  const int tid = threadIdx.x;
+  const int n0 = blockIdx.y * kOwN, k0 = blockIdx.x * kOwK;
+  for (int e = tid; e < B * kOwN; e += 256) {
+    const int b = e / kOwN, n = e % kOwN;
+    sdy[b][n] = (n0 + n < N) ? to_f(dy[(int64_t)b * ld_dy + n0 + n]) : 0.f;
+  }
+  for (int e = tid; e < B * kOwK; e += 256) {
+    const int b = e / kOwK, k = e % kOwK;
+    sx[b][k] = (k0 + k < K) ? to_f(x[(int64_t)b * ld_x + k0 + k]) : 0.f;
+  }
+  __syncthreads();
+  const int tk = (tid & 31) * 4, tn = (tid >> 5) * 4;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  for (int b = 0; b < B; ++b) {
+    const float4 a4 = *reinterpret_cast<const float4*>(&sdy[b][tn]);     // same address across the warp: broadcast
+    const float4 x4 = *reinterpret_cast<const float4*>(&sx[b][tk]);
+    const float a[4] = {a4.x, a4.y, a4.z, a4.w}, xv[4] = {x4.x, x4.y, x4.z, x4.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], xv[j], acc[i][j]);
+  }
+  const int col = k0 + tk;
+  if (col >= K) return;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int row = n0 + tn + i;
+    if (row >= N) continue;
+    float* d = D + (int64_t)row * ldd + col;
+    F4 o{{acc[i][0], acc[i][1], acc[i][2], acc[i][3]}};
+    if (accumulate) {
+      const F4 old = load4(d);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) o.v[j] += old.v[j];
+    }
+    store4(d, o);
+  }
+}
+
+// D[M_out = N of dy, N_out = K of x]: called through gemm_simt's interface (a_mn && b_mn, contraction <= 64)
+static int outer_wgrad(int act_dtype, const void* A, int64_t lda, const void* B, int64_t ldb, float* D, int64_t ldd, int M,
+                       int N, int K, int accumulate, cudaStream_t st) {
+  dim3 grid(ceil_div(N, kOwK), ceil_div(M, kOwN));
+  if (act_dtype == kBF16)
+    outer_wgrad_kernel<bf16><<<grid, 256, 0, st>>>((const bf16*)A, lda, (const bf16*)B, ldb, D, ldd, M, N, K, accumulate);
+  else
+    outer_wgrad_kernel<float><<<grid, 256, 0, st>>>((const float*)A, lda, (const float*)B, ldb, D, ldd, M, N, K, accumulate);
+  REED_LAUNCH_CHECK();
+  return 0;
+}
+
 int gemm_simt(int act_dtype, const void* A, int64_t lda, int a_mn, const void* B, int64_t ldb, int b_mn, void* D,
               int64_t ldd, int d_dtype, int M, int N, int K, const EpiParams& ep, cudaStream_t st) {
   REED_REQUIRE(N % 4 == 0 && ldd % 4 == 0, "gemm_simt needs N %% 4 == 0 and ldd %% 4 == 0 (N=%d ldd=%lld)", N, (long long)ldd);
+  // batch-contraction weight gradient (A = dy stored [K, M], B = x stored [K, N], K <= 64 rows): outer-product stream
+  if (a_mn && b_mn && K <= 64 && d_dtype == kF32 && ep.kind == kEpiNone && ep.bias == nullptr && (int64_t)M * N >= 65536)
+    return outer_wgrad(act_dtype, A, lda, B, ldb, (float*)D, ldd, M, N, K, ep.accumulate, st);
   dim3 grid(ceil_div(N, SBN), ceil_div(M, SBM));
   int k_per_split = K > 0 ? K : 1;
   // few output tiles and a long reduction (patch-embed / final-layer wgrad): split K across the machine

@@ -142,13 +142,13 @@ class SiTBlock(nn.Module):
     def forward(self, x, c_act, act_dtype, c_acc=None):
         """x: (N,T,D) fp32; c_act = silu(c) already in the act dtype (shared by every block); c_acc: the side
         accumulator the block adds its gradient w.r.t. c_act into (ops.silu_cast)."""
-        if self.qk_norm:
-            raise NotImplementedError("qk_norm=True is not wired to the CUDA attention kernels yet")
         lin = self.adaLN_modulation[1]
         a, m = self.attn, self.mlp
         return ops.SiTBlockFn.apply(x, c_act, lin.weight, lin.bias, a.qkv.weight, a.qkv.bias, a.proj.weight, a.proj.bias,
                                     m.fc1.weight, m.fc1.bias, m.fc2.weight, m.fc2.bias, self.num_heads, act_dtype,
-                                    getattr(self, "_reed_after_backward", None), c_acc)
+                                    getattr(self, "_reed_after_backward", None), c_acc,
+                                    *((a.q_norm.weight, a.q_norm.bias, a.k_norm.weight, a.k_norm.bias) if self.qk_norm
+                                      else ()))
 
 
 class FinalLayer(nn.Module):

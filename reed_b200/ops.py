@@ -185,6 +185,22 @@ def gate_bwd(dxn, y, gate, rows_per_group, dgate, dbias):
     return dy
 
 
+def qk_norm_fwd(qkv, wq, bq, wk, bk, rows, H, hd, eps=1e-5):
+    """LayerNorm(head_dim) of the q and k thirds of the packed qkv (timm Attention q_norm/k_norm); v copied through."""
+    out = torch.empty_like(qkv)
+    stats = torch.empty((rows, H, 2, 2), device=qkv.device, dtype=torch.float32)
+    _launch("reed_qk_norm_fwd", _p(qkv), _code(qkv.dtype), _p(wq), _p(bq), _p(wk), _p(bk), _p(out), _p(stats), rows, H, hd,
+            eps, _stream())
+    return out, stats
+
+
+def qk_norm_bwd(dout, qkv, stats, wq, wk, dwq, dbq, dwk, dbk, rows, H, hd):
+    dqkv = torch.empty_like(qkv)
+    _launch("reed_qk_norm_bwd", _p(dout), _code(dout.dtype), _p(qkv), _p(stats), _p(wq), _p(wk), _p(dqkv), _p(dwq), _p(dbq),
+            _p(dwk), _p(dbk), rows, H, hd, _stream())
+    return dqkv
+
+
 def attention_fwd(qkv, B, T, H, hd):
     o = torch.empty((B * T, H * hd), device=qkv.device, dtype=qkv.dtype)
     lse = torch.empty((B, H, T), device=qkv.device, dtype=torch.float32)
@@ -392,7 +408,7 @@ class SiTBlockFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, c_act, w_ada, b_ada, w_qkv, b_qkv, w_proj, b_proj, w_fc1, b_fc1, w_fc2, b_fc2, num_heads,
-                act_dtype, after_backward, c_acc=None):
+                act_dtype, after_backward, c_acc=None, qn_w=None, qn_b=None, kn_w=None, kn_b=None):
         _require_cuda(x, c_act)
         B, T, D = x.shape
         M = B * T
@@ -404,7 +420,12 @@ class SiTBlockFn(torch.autograd.Function):
         mod = gemm(c_act, W(w_ada), out_dtype=torch.float32, bias=b_ada.detach())
         sh_a, sc_a, g_a, sh_m, sc_m, g_m = (mod[:, i * D:(i + 1) * D] for i in range(6))
         xm1, mean1, rstd1 = ln_modulate_fwd(x0, sh_a, sc_a, T, act_dtype)
-        qkv = gemm(xm1, W(w_qkv), out_dtype=act_dtype, bias=b_qkv.detach())
+        qkv_raw = gemm(xm1, W(w_qkv), out_dtype=act_dtype, bias=b_qkv.detach())
+        qk_stats = None
+        qkv = qkv_raw
+        if qn_w is not None:      # timm Attention(qk_norm=True): LayerNorm(head_dim) on q and k before the softmax
+            qkv, qk_stats = qk_norm_fwd(qkv_raw, qn_w.detach().float(), qn_b.detach().float(), kn_w.detach().float(),
+                                        kn_b.detach().float(), M, H, hd)
         o, lse = attention_fwd(qkv, B, T, H, hd)
         y1 = torch.empty((M, D), device=x.device, dtype=act_dtype)
         x1 = gemm(o, W(w_proj), out_dtype=torch.float32, bias=b_proj.detach(), epilogue=EPI_GATE_RES, aux=x0, gate=g_a,
@@ -416,8 +437,10 @@ class SiTBlockFn(torch.autograd.Function):
         x2 = gemm(a, W(w_fc2), out_dtype=torch.float32, bias=b_fc2.detach(), epilogue=EPI_GATE_RES, aux=x1, gate=g_m,
                   rows_per_group=T, out2=y2)
 
-        ctx.save_for_backward(x0, c_act, mod, mean1, rstd1, xm1, qkv, o, lse, y1, x1, mean2, rstd2, xm2, h, a, y2)
+        ctx.save_for_backward(x0, c_act, mod, mean1, rstd1, xm1, qkv, o, lse, y1, x1, mean2, rstd2, xm2, h, a, y2,
+                              qkv_raw if qk_stats is not None else None, qk_stats)
         ctx.params = (w_ada, b_ada, w_qkv, b_qkv, w_proj, b_proj, w_fc1, b_fc1, w_fc2, b_fc2)
+        ctx.qk_params = (qn_w, qn_b, kn_w, kn_b)
         ctx.dims = (B, T, D, H, hd)
         ctx.act_dtype = act_dtype
         ctx.after_backward = after_backward
@@ -426,7 +449,8 @@ class SiTBlockFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dx2):
-        x0, c_act, mod, mean1, rstd1, xm1, qkv, o, lse, y1, x1, mean2, rstd2, xm2, h, a, y2 = ctx.saved_tensors
+        (x0, c_act, mod, mean1, rstd1, xm1, qkv, o, lse, y1, x1, mean2, rstd2, xm2, h, a, y2, qkv_raw,
+         qk_stats) = ctx.saved_tensors
         w_ada, b_ada, w_qkv, b_qkv, w_proj, b_proj, w_fc1, b_fc1, w_fc2, b_fc2 = ctx.params
         B, T, D, H, hd = ctx.dims
         M = B * T
@@ -462,6 +486,17 @@ class SiTBlockFn(torch.autograd.Function):
         dwp = _weight_grad(w_proj, dy1, o)
         d_o = gemm(dy1, W(w_proj), b_mn=True, out_dtype=act_dtype)
         dqkv = attention_bwd(qkv, o, d_o, lse, B, T, H, hd)
+        qk_grads = (None, None, None, None)
+        if qk_stats is not None:
+            qn_w, qn_b, kn_w, kn_b = ctx.qk_params
+            bufs, rets = [], []
+            for prm in (qn_w, qn_b, kn_w, kn_b):
+                buf, ret = bias_buffer(prm)
+                bufs.append(buf)
+                rets.append(ret)
+            dqkv = qk_norm_bwd(dqkv, qkv_raw, qk_stats, qn_w.detach().float(), kn_w.detach().float(), bufs[0], bufs[1],
+                               bufs[2], bufs[3], M, H, hd)
+            qk_grads = tuple(rets)
         dbqkv = _bias_grad(b_qkv, dqkv)
         dwqkv = _weight_grad(w_qkv, dqkv, xm1)
         dxm1 = gemm(dqkv, W(w_qkv), b_mn=True, out_dtype=act_dtype)
@@ -480,7 +515,7 @@ class SiTBlockFn(torch.autograd.Function):
 
         if ctx.after_backward is not None:
             ctx.after_backward()
-        return (dx0.view(B, T, D), dc, dw_ada, db_ada, dwqkv, dbqkv, dwp, dbp, dw1, db1, dw2, db2, None, None, None, None)
+        return (dx0.view(B, T, D), dc, dw_ada, db_ada, dwqkv, dbqkv, dwp, dbp, dw1, db1, dw2, db2, None, None, None, None) + qk_grads
 
 
 # --------------------------------------------------------------------------------------------------

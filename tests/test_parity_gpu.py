@@ -109,6 +109,41 @@ def test_loss_and_gradients_match_reference_golden(golden, name, precision, loss
     assert _rel(pred, case["eval_pred"]) < (2e-5 if precision == "fp32" else 3e-2)
 
 
+@pytest.mark.parametrize("precision,loss_tol,cos_min", [("fp32", 1e-5, 0.99999), ("bf16", 2e-2, 0.999)])
+def test_qk_norm_and_time_schedules_match_reference_golden(golden, precision, loss_tol, cos_min):
+    """qk_norm=True (timm Attention q_norm/k_norm LayerNorm kernels) under every time schedule, against the golden
+    losses of the unmodified reference; gradients of the last case against autograd over the CPU oracle."""
+    for schedule, case in golden("loss_c_schedules.pt").items():
+        spec, sd, data, model, out = _run_case(case, precision)
+        assert spec.qk_norm
+        assert _rel(out["denoising_loss"], case["denoising_loss"]) < loss_tol, schedule
+        # a zero base weight makes proj_loss tiny; compare on the scale of the per-sample alignment instead
+        scale = float(case["saver_image"].abs().max())
+        assert abs(float(out["proj_loss"]) - float(case["proj_loss"])) < loss_tol * max(scale, 1e-3), schedule
+        assert _rel(out["loss_saver"]["image"], case["saver_image"]) < loss_tol, schedule
+    total = out["denoising_loss"].mean() + 0.5 * out["proj_loss"]
+    total.backward()
+    leaves = {k: v.clone().requires_grad_(k != "pos_embed") for k, v in sd.items()}
+    ref_model = sit_oracle.as_model(leaves, spec, training=True, drop_mask=case["drop"])
+    ref = loss_oracle.si_loss(ref_model, data["x"], case["t"], case["noise"], data["zs"], enc_names=case["enc_names"],
+                              loss_weights=case["loss_weights"], model_kwargs=dict(y=data["y"]),
+                              path_type=case["path_type"], time_schedule=case["time_schedule"], cutoffs=case["cutoffs"])
+    (ref["denoising_loss"].mean() + 0.5 * ref["proj_loss"]).backward()
+    got = {n: p.grad for n, p in model.named_parameters() if p.grad is not None}
+    checked = 0
+    for k, leaf in leaves.items():
+        if leaf.grad is None:
+            continue
+        if float(leaf.grad.norm()) < 1e-6:
+            # exactly zero in exact arithmetic (k_norm.bias shifts every logit of a row by the same q.b): noise only
+            assert float(got[k].norm()) < (1e-5 if precision == "fp32" else 1e-2), k
+            continue
+        cos = float(F.cosine_similarity(got[k].flatten().double().cpu(), leaf.grad.flatten().double(), dim=0))
+        assert cos >= cos_min, (k, cos)
+        checked += 1
+    assert any("q_norm" in k for k in got) and any("k_norm.bias" in k for k in got) and checked > 20
+
+
 def test_time_schedules_broadcast_quirk():
     # direct check of the quirk on device with an analytic stand-in for the model
     from reed_b200.image.loss import SILoss
