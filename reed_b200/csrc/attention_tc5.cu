@@ -668,6 +668,8 @@ attn_tc5_dkv_kernel(const __grid_constant__ AttnMaps maps, const float* __restri
 
   if (warp == 8) {
     const bool leader = elect_one();
+    TRACE_DECL(2, lane == 0);
+    TRACE(1);
     if (leader) {
       mbar_expect_tx(bar_kv, 2 * TL::kBytes);
       load_tile<HD>(&maps.qkv_main, &maps.qkv_tail, bar_kv, sK, H + h, row0);
@@ -680,8 +682,10 @@ attn_tc5_dkv_kernel(const __grid_constant__ AttnMaps maps, const float* __restri
     }
     __syncwarp();
     mbar_wait(bar_kv, 0);
+    TRACE(2);
     for (int i = 0; i < nblk; ++i) {
       mbar_wait(&bar_q[i], 0);
+      TRACE(3);
       tc_fence_after();
       mma_scores<HD>(leader, tmem + i * 256, sK, sQ + i * TL::kBytes);            // S^T_i = K Q_i^T
       mma_scores<HD>(leader, tmem + i * 256 + 128, sV, sDO + i * TL::kBytes);     // dP^T_i = V dO_i^T
@@ -689,10 +693,12 @@ attn_tc5_dkv_kernel(const __grid_constant__ AttnMaps maps, const float* __restri
     }
     for (int i = 0; i < nblk; ++i) {                  // dV -> columns 0.. (dead S^T_0), dK -> columns 128.. (dead dP^T_0)
       mbar_wait(&bar_p[i], 0);
+      TRACE(4);
       tc_fence_after();
       const uint32_t pt = sBuf + (i == 0 ? 0 : 2 * kPBytes), dst = i == 0 ? sBuf + kPBytes : sK;
       mma_accum<HD>(leader, tmem, pt, sDO + i * TL::kBytes, i > 0);
       mma_accum<HD>(leader, tmem + 128, dst, sQ + i * TL::kBytes, i > 0);
+      TRACE(5);
     }
     commit_if(leader, bar_acc);
     __syncwarp();
@@ -700,11 +706,14 @@ attn_tc5_dkv_kernel(const __grid_constant__ AttnMaps maps, const float* __restri
     const int g = warp >> 2;
     const int row = (warp & 3) * 32 + lane;
     const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+    TRACE_DECL(g, (warp & 3) == 0 && lane == 0);
+    TRACE(1);
     if (g < nblk) {
       // dS^T_1 overwrites K and V: every score MMA (both blocks) must have retired
       mbar_wait(&bar_s[g], 0);
       if (g == 1) mbar_wait(&bar_s[0], 0);
       tc_fence_after();
+      TRACE(2);
       const uint32_t pt = sBuf + (g == 0 ? 0 : 2 * kPBytes), dst = g == 0 ? sBuf + kPBytes : sK;
       const float* L = sL + g * kRows;
       const float* Dl = sD + g * kRows;
@@ -732,9 +741,11 @@ attn_tc5_dkv_kernel(const __grid_constant__ AttnMaps maps, const float* __restri
       fence_proxy_async();
       tc_fence_before();
       mbar_arrive(&bar_p[g]);
+      TRACE(3);
     }
     mbar_wait(bar_acc, 0);
     tc_fence_after();
+    TRACE(4);
     // group 0 stages and stores dV (over Q_0), group 1 dK (over Q_1)
     const uint32_t stage = sQ + g * TL::kBytes;
     stage_acc_row<HD>(trow + g * 128, g == 0 ? 1.f : scale, stage, row, 0, HD);
@@ -745,6 +756,7 @@ attn_tc5_dkv_kernel(const __grid_constant__ AttnMaps maps, const float* __restri
       tma_store_commit();
       tma_store_wait_read();
     }
+    TRACE(5);
   }
   tc_fence_before();
   __syncthreads();

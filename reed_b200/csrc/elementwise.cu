@@ -47,8 +47,10 @@ __device__ __forceinline__ void row_bulk_load(void* dst, const void* src, uint32
 
 // ---------------------------------------------------------------------------------------------
 // out[m,:] = LN(x[m,:]) * (1 + scale[g,:]) + shift[g,:],  g = m / rows_per_group
-// One warp per row at a time; each warp streams its rows (row, row + total_warps, ...) through a private ring of
-// kRowStages shared-memory row buffers filled by bulk copies it issues itself.
+// A CTA owns `rows_per_cta` consecutive rows of ONE group: the group's shift and 1 + scale vectors are staged in shared
+// memory once (they would otherwise be 2 dependent global loads per column group per row).  One warp per row at a
+// time; every warp streams its rows (r0 + warp, r0 + warp + kLnWarps, ...) through a private ring of kLnStages
+// shared-memory row buffers filled by bulk copies it issues itself.
 // ---------------------------------------------------------------------------------------------
 constexpr int kLnWarps = 8;
 constexpr int kLnStages = 2;
@@ -56,31 +58,47 @@ constexpr int kLnStages = 2;
 template <typename TA, int MAXV>
 __global__ void __launch_bounds__(kLnWarps * 32) ln_modulate_fwd_kernel(
     const float* __restrict__ x, const float* __restrict__ shift, const float* __restrict__ scale, int64_t ld_mod,
-    int rows_per_group, TA* __restrict__ out, float* __restrict__ mean_out, float* __restrict__ rstd_out, int M, int D,
-    float eps) {
+    int rows_per_group, int rows_per_cta, TA* __restrict__ out, float* __restrict__ mean_out,
+    float* __restrict__ rstd_out, int M, int D, float eps) {
   extern __shared__ __align__(128) uint8_t ln_smem[];
   __shared__ uint64_t bars[kLnWarps][kLnStages];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int total_warps = gridDim.x * kLnWarps;
-  const int first = blockIdx.x * kLnWarps + warp;
+  const int r0 = blockIdx.x * rows_per_cta;
+  const int r1 = min(r0 + rows_per_cta, M);
   float* ring = reinterpret_cast<float*>(ln_smem) + (size_t)warp * kLnStages * D;
+  float* s_shift = reinterpret_cast<float*>(ln_smem) + (size_t)kLnWarps * kLnStages * D;
+  float* s_scale1 = s_shift + D;
   const uint32_t row_bytes = (uint32_t)D * 4u;
+  const int first = r0 + warp;
   if (lane == 0) {
 #pragma unroll
     for (int s = 0; s < kLnStages; ++s) row_bar_init(&bars[warp][s]);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 #pragma unroll
     for (int s = 0; s < kLnStages; ++s) {
-      const int row = first + s * total_warps;
-      if (row < M) {
+      const int row = first + s * kLnWarps;
+      if (row < r1) {
         row_bar_expect(&bars[warp][s], row_bytes);
         row_bulk_load(ring + (size_t)s * D, x + (int64_t)row * D, row_bytes, &bars[warp][s]);
       }
     }
   }
-  __syncwarp();
+  {
+    const int g = r0 / rows_per_group;
+    const float* sh = shift + (int64_t)g * ld_mod;
+    const float* sc = scale + (int64_t)g * ld_mod;
+    for (int c = threadIdx.x * 4; c < D; c += kLnWarps * 32 * 4) {
+      const F4 a = load4(sh + c);
+      F4 b = load4(sc + c);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b.v[j] += 1.f;
+      store4(s_shift + c, a);
+      store4(s_scale1 + c, b);
+    }
+  }
+  __syncthreads();
   int it = 0;
-  for (int row = first; row < M; row += total_warps, ++it) {
+  for (int row = first; row < r1; row += kLnWarps, ++it) {
     const int slot = it % kLnStages;
     row_bar_wait(&bars[warp][slot], (uint32_t)(it / kLnStages) & 1u);
     const float* xr = ring + (size_t)slot * D;
@@ -96,8 +114,8 @@ __global__ void __launch_bounds__(kLnWarps * 32) ln_modulate_fwd_kernel(
     }
     __syncwarp();          // every lane has its values in registers: the slot can be refilled
     if (lane == 0) {
-      const int nrow = row + kLnStages * total_warps;
-      if (nrow < M) {
+      const int nrow = row + kLnStages * kLnWarps;
+      if (nrow < r1) {
         row_bar_expect(&bars[warp][slot], row_bytes);
         row_bulk_load(ring + (size_t)slot * D, x + (int64_t)nrow * D, row_bytes, &bars[warp][slot]);
       }
@@ -120,17 +138,15 @@ __global__ void __launch_bounds__(kLnWarps * 32) ln_modulate_fwd_kernel(
       mean_out[row] = mean;
       rstd_out[row] = rstd;
     }
-    const int g = row / rows_per_group;
-    const float* sh = shift + (int64_t)g * ld_mod;
-    const float* sc = scale + (int64_t)g * ld_mod;
     TA* o = out + (int64_t)row * D;
 #pragma unroll
     for (int i = 0; i < MAXV; ++i) {
       int col = (i * 32 + lane) * 4;
       if (col < D) {
-        F4 a = load4(sh + col), b = load4(sc + col), r;
+        const F4 a = load4(s_shift + col), b = load4(s_scale1 + col);
+        F4 r;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) r.v[j] = (c[i].v[j] - mean) * rstd * (1.f + b.v[j]) + a.v[j];
+        for (int j = 0; j < 4; ++j) r.v[j] = (c[i].v[j] - mean) * rstd * b.v[j] + a.v[j];
         store4(o + col, r);
       }
     }
@@ -500,20 +516,17 @@ template <typename TA, int V>
 static int ln_fwd_launch(const float* x, const float* shift, const float* scale, int64_t ld_mod, int rpg, void* out,
                          float* mean, float* rstd, int M, int D, float eps, cudaStream_t st) {
   auto kernel = ln_modulate_fwd_kernel<TA, V>;
-  const int smem = kLnWarps * kLnStages * D * 4;
+  const int smem = (kLnWarps * kLnStages + 2) * D * 4;
   static int configured = 0;
   if (configured < smem) {
     REED_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = smem;
   }
-  // persistent: as many CTAs as fit (shared memory bound), every warp strides over the rows
-  int per_sm = (226 * 1024) / (smem + 1024);
-  if (per_sm > 8) per_sm = 8;
-  if (per_sm < 1) per_sm = 1;
-  int grid = row_sm_count() * per_sm;
-  const int need = ceil_div(M, kLnWarps);
-  if (grid > need) grid = need;
-  kernel<<<grid, kLnWarps * 32, smem, st>>>(x, shift, scale, ld_mod, rpg, (TA*)out, mean, rstd, M, D, eps);
+  // row ranges never straddle a group: the largest power of two <= 32 that divides rows_per_group, shrunk until the
+  // grid covers every SM at least twice
+  int rows = 32;
+  while (rows > 1 && (rpg % rows != 0 || ceil_div(M, rows) < 2 * row_sm_count())) rows >>= 1;
+  kernel<<<ceil_div(M, rows), kLnWarps * 32, smem, st>>>(x, shift, scale, ld_mod, rpg, rows, (TA*)out, mean, rstd, M, D, eps);
   REED_LAUNCH_CHECK();
   return 0;
 }
