@@ -22,6 +22,8 @@ def main():
     ap.add_argument("--tokens", type=int, default=8192)
     ap.add_argument("--iters", type=int, default=20)
     ap.add_argument("--only", default=None, help="substring filter on the case name")
+    ap.add_argument("--cublas", action="store_true",
+                    help="also time torch.matmul (cuBLAS, no epilogue) on the same operands: a yardstick, not the product path")
     args = ap.parse_args()
     _cabi.load()
     D = {"xl": 1152, "b": 768, "l": 1024, "s": 384}[args.model]
@@ -56,10 +58,39 @@ def main():
         ("proj wgrad", D, D, M, lambda: ops.gemm(dyd, x, a_mn=True, b_mn=True, out=g_proj)),
         ("qkv wgrad", 3 * D, D, M, lambda: ops.gemm(dy3, x, a_mn=True, b_mn=True, out=g_qkv)),
     ]
-    total_us, total_fl = 0.0, 0.0
+    # the plain contraction of each case as cuBLAS sees it (bf16 out, no bias / epilogue / accumulation)
+    cublas = {
+        "qkv fwd   +bias": lambda: torch.matmul(x, w_qkv.t()), "proj fwd  gate+res": lambda: torch.matmul(x, w_proj.t()),
+        "fc1 fwd   gelu": lambda: torch.matmul(x, w_fc1.t()), "fc2 fwd   gate+res": lambda: torch.matmul(x4, w_fc2.t()),
+        "fc2 dgrad dgelu": lambda: torch.matmul(dyd, w_fc2), "fc1 dgrad": lambda: torch.matmul(dy4, w_fc1),
+        "proj dgrad": lambda: torch.matmul(dyd, w_proj), "qkv dgrad": lambda: torch.matmul(dy3, w_qkv),
+        "fc2 wgrad": lambda: torch.matmul(dyd.t(), x4), "fc1 wgrad": lambda: torch.matmul(dy4.t(), x),
+        "proj wgrad": lambda: torch.matmul(dyd.t(), x), "qkv wgrad": lambda: torch.matmul(dy3.t(), x),
+    }
+
+    def median_us(fn):
+        for _ in range(3):
+            fn()
+        ts = []
+        for _ in range(args.iters):
+            flush.sum()
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            fn()
+            e.record()
+            torch.cuda.synchronize()
+            ts.append(s.elapsed_time(e) * 1e3)
+        ts.sort()
+        return ts[len(ts) // 2]
+
+    total_us, total_fl, total_cb = 0.0, 0.0, 0.0
     for name, m, n, k, fn in cases:
         if args.only and args.only not in name:
             continue
+        if args.cublas:
+            cb = median_us(cublas[name])
+            total_cb += cb
+            print(f"{name:20s} cuBLAS plain matmul      {cb:8.1f} us  {2.0 * m * n * k / cb / 1e6:7.1f} TFLOP/s")
         for _ in range(3):
             fn()
         ts = []
@@ -78,6 +109,8 @@ def main():
         total_fl += fl
         print(f"{name:20s} M={m:5d} N={n:5d} K={k:5d}  {us:8.1f} us  {fl / us / 1e6:7.1f} TFLOP/s")
     print(f"block total {total_us:8.1f} us  {total_fl / total_us / 1e6:7.1f} TFLOP/s")
+    if args.cublas and total_cb:
+        print(f"cuBLAS plain total {total_cb:8.1f} us  {total_fl / total_cb / 1e6:7.1f} TFLOP/s")
 
 
 if __name__ == "__main__":

@@ -9,7 +9,8 @@ import os
 from ctypes import c_char_p, c_double, c_float, c_int, c_int64, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libreed_sm100.so")
+# REED_LIB: profiling knob - load an experimental build of the same library (profiles/*.py variants)
+LIB_PATH = os.environ.get("REED_LIB") or os.path.join(_HERE, "libreed_sm100.so")
 
 P, I, L, F, D = c_void_p, c_int, c_int64, c_float, c_double
 
