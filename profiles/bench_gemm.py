@@ -22,6 +22,8 @@ def main():
     ap.add_argument("--tokens", type=int, default=8192)
     ap.add_argument("--iters", type=int, default=20)
     ap.add_argument("--only", default=None, help="substring filter on the case name")
+    ap.add_argument("--no-flush", action="store_true", help="leave L2 warm between iterations")
+    ap.add_argument("--bn", type=int, default=0, help="pin the tile width (128/192/256)")
     ap.add_argument("--cublas", action="store_true",
                     help="also time torch.matmul (cuBLAS, no epilogue) on the same operands: a yardstick, not the product path")
     args = ap.parse_args()
@@ -29,7 +31,7 @@ def main():
     D = {"xl": 1152, "b": 768, "l": 1024, "s": 384}[args.model]
     M, T = args.tokens, 256
     dev = "cuda"
-    ops.set_backends(gemm=ops.BACKEND_TENSOR)
+    ops.set_backends(gemm=ops.BACKEND_TENSOR + ({0: 0, 128: 1, 192: 2, 256: 3}[args.bn] << 3))
     bf = torch.bfloat16
     r = lambda *s, dt=bf: (torch.randn(*s, device=dev) * 0.05).to(dt)
     flush = torch.zeros(64 << 20, dtype=torch.int32, device=dev)
@@ -73,7 +75,8 @@ def main():
             fn()
         ts = []
         for _ in range(args.iters):
-            flush.sum()
+            if not args.no_flush:
+                flush.sum()
             s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             s.record()
             fn()
@@ -95,7 +98,8 @@ def main():
             fn()
         ts = []
         for _ in range(args.iters):
-            flush.sum()            # read-only L2 flush: leaves clean lines, no write-back competing with the timed kernel
+            if not args.no_flush:
+                flush.sum()        # read-only L2 flush: leaves clean lines, no write-back competing with the timed kernel
             s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             s.record()
             fn()

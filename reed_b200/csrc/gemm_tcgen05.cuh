@@ -62,15 +62,15 @@ struct Seg { int tile, kb0, kb1, half; };   // half: the tile is the ragged last
 struct Sched {
   int sk, num_tiles, num_kb, tiles_n, ragged, round;
   int64_t u, u_end;
-  int worker, stride;
+  int worker, stride, colmajor;
   // `worker` = index of this CTA (CG = 1) or CTA pair (CG = 2) among `workers`.
   // Data-parallel order: all full-width tiles first (row-major), then the ragged last-column tiles (when N leaves a
   // remainder of at most BN/2 they are computed with a BN/2-wide MMA and cost half a tile); rounds alternate
   // direction over the workers (snake), so the half tiles of the last rounds land on the workers that got one
   // tile less - e.g. N = 1152, BN = 256, M = 8192: 128 full + 32 half tiles on 74 pairs take 2 tile times, not 3.
-  __device__ Sched(int sk_, int tiles_m, int tiles_n_, int ragged_, int num_kb_, int worker_, int workers)
+  __device__ Sched(int sk_, int tiles_m, int tiles_n_, int ragged_, int num_kb_, int worker_, int workers, int colmajor_ = 0)
       : sk(sk_), num_tiles(tiles_m * tiles_n_), num_kb(num_kb_), tiles_n(tiles_n_), ragged(ragged_), round(0),
-        worker(worker_), stride(workers) {
+        worker(worker_), stride(workers), colmajor(colmajor_) {
     const int64_t total = (int64_t)num_tiles * num_kb;
     u = total * worker / workers;
     u_end = total * (worker + 1) / workers;
@@ -80,6 +80,11 @@ struct Sched {
       const int v = round * stride + ((round & 1) ? stride - 1 - worker : worker);
       if (v >= num_tiles) return false;
       ++round;
+      if (colmajor) {   // profiling knob: walk the tiles down the columns (ragged handling off)
+        const int tm = num_tiles / tiles_n;
+        s.tile = (v % tm) * tiles_n + v / tm; s.half = 0; s.kb0 = 0; s.kb1 = num_kb;
+        return true;
+      }
       const int n_full = tiles_n - ragged;
       const int count_full = (num_tiles / tiles_n) * n_full;
       if (v < count_full) { s.tile = (v / n_full) * tiles_n + (v % n_full); s.half = 0; }
@@ -236,7 +241,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                     TD* __restrict__ D, int64_t ldd, int M, int N, int K, EpiParams ep, int stream_k, int dbg) {
   // dbg (profiling only, results are garbage): 1 = no TMA (MMA does not wait for operands), 2 = no MMA issue,
-  // 4 = no epilogue work (accumulators released immediately)
+  // 4 = no epilogue work (accumulators released immediately); 8 = column-major tile order (results stay correct)
   using Cfg = GemmCfg<CG, BN>;
   constexpr int S = Cfg::kStages;
   constexpr int BNL = Cfg::kBNL;
@@ -261,7 +266,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   const int tiles_m = (M + BMT - 1) / BMT, tiles_n = (N + BN - 1) / BN;
   const int num_kb = (K + BK - 1) / BK;
   const int n_rem = N - (tiles_n - 1) * BN;    // width of the last column tile
-  const int ragged = (!stream_k && half_tile_ok<CG, BN, B_MN>() && n_rem <= BN / 2) ? 1 : 0;
+  const int ragged = (!stream_k && !(dbg & 8) && half_tile_ok<CG, BN, B_MN>() && n_rem <= BN / 2) ? 1 : 0;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_a);
@@ -285,64 +290,83 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 0 && lane == 0) {
+  // The TMA and MMA warps run warp-uniform code: all 32 lanes walk the schedule and poll the barriers, one elected
+  // lane executes the TMA / tcgen05 instructions.  Those take their operands from uniform registers; issued from a
+  // single-lane divergent branch every one of them is wrapped in an R2UR "waterfall" loop of ~25 dependent
+  // instructions, which costs more than the 64..128 cycles an MMA occupies the tensor pipe.
+  if (warp == 0) {
     // ============================== TMA producer (every CTA loads its own A rows / B rows) ==============================
+    const bool issuer = elect_one_sync();
     int stage = 0;
     uint32_t phase = 0;
-    Sched sched(stream_k, tiles_m, tiles_n, ragged, num_kb, worker, workers);
+    Sched sched(stream_k, tiles_m, tiles_n, ragged, num_kb, worker, workers, (dbg >> 3) & 1);
     Seg sg;
+    const uint32_t stage0 = smem_u32(stage_base);
+    const uint32_t full0 = smem_u32(full);
     while (!(dbg & 1) && sched.next(sg)) {
       const int m0 = (sg.tile / tiles_n) * BMT + (int)rank * BM;
       // a half tile is BN/2 wide: each CTA of the pair supplies BN/2/CG rows of B, taken from the head of its box
       const int n0 = (sg.tile % tiles_n) * BN + (int)rank * (sg.half ? BNL / 2 : BNL);
       for (int kb = sg.kb0; kb < sg.kb1; ++kb) {
         mbar_wait(&empty[stage], phase ^ 1);
-        uint8_t* sa = stage_base + stage * Cfg::kStageBytes;
-        uint8_t* sb = sa + Cfg::kABytes;
+        const uint32_t sa = stage0 + stage * Cfg::kStageBytes;
+        const uint32_t sb = sa + Cfg::kABytes;
+        const uint32_t fbar = full0 + stage * 8;
         const int k0 = kb * BK;
-        if constexpr (CG == 1) {
-          mbar_expect_tx(&full[stage], Cfg::kStageBytes);
-          if (A_MN) {
+        if (issuer) {
+          if constexpr (CG == 1) {
+            mbar_expect_tx_u32(fbar, Cfg::kStageBytes);
+            if (A_MN) {
 #pragma unroll
-            for (int c = 0; c < BM / 64; ++c) tma_load_2d(&map_a, &full[stage], sa + c * (BK * 128), m0 + c * 64, k0);
-          } else {
-            tma_load_2d(&map_a, &full[stage], sa, k0, m0);
-          }
-          if (B_MN) {
+              for (int c = 0; c < BM / 64; ++c) tma_load_2d_u32(&map_a, fbar, sa + c * (BK * 128), m0 + c * 64, k0);
+            } else {
+              tma_load_2d_u32(&map_a, fbar, sa, k0, m0);
+            }
+            if (B_MN) {
 #pragma unroll
-            for (int c = 0; c < BNL / 64; ++c) tma_load_2d(&map_b, &full[stage], sb + c * (BK * 128), n0 + c * 64, k0);
+              for (int c = 0; c < BNL / 64; ++c) tma_load_2d_u32(&map_b, fbar, sb + c * (BK * 128), n0 + c * 64, k0);
+            } else {
+              tma_load_2d_u32(&map_b, fbar, sb, k0, n0);
+            }
           } else {
-            tma_load_2d(&map_b, &full[stage], sb, k0, n0);
-          }
-        } else {
-          if (leader) mbar_expect_tx(&full[stage], CG * Cfg::kStageBytes);
-          const uint32_t fb = mapa_u32(smem_u32(&full[stage]), 0);
-          if (A_MN) {
+            if (leader) mbar_expect_tx_u32(fbar, CG * Cfg::kStageBytes);
+            const uint32_t fb = mapa_u32(fbar, 0);
+            if (A_MN) {
 #pragma unroll
-            for (int c = 0; c < BM / 64; ++c) tma_load_2d_cg2(&map_a, fb, sa + c * (BK * 128), m0 + c * 64, k0);
-          } else {
-            tma_load_2d_cg2(&map_a, fb, sa, k0, m0);
-          }
-          if (B_MN) {
+              for (int c = 0; c < BM / 64; ++c) tma_load_2d_cg2_u32(&map_a, fb, sa + c * (BK * 128), m0 + c * 64, k0);
+            } else {
+              tma_load_2d_cg2_u32(&map_a, fb, sa, k0, m0);
+            }
+            if (B_MN) {
 #pragma unroll
-            for (int c = 0; c < BNL / 64; ++c) tma_load_2d_cg2(&map_b, fb, sb + c * (BK * 128), n0 + c * 64, k0);
-          } else {
-            tma_load_2d_cg2(&map_b, fb, sb, k0, n0);
+              for (int c = 0; c < BNL / 64; ++c) tma_load_2d_cg2_u32(&map_b, fb, sb + c * (BK * 128), n0 + c * 64, k0);
+            } else {
+              tma_load_2d_cg2_u32(&map_b, fb, sb, k0, n0);
+            }
           }
         }
+        __syncwarp();
         if (++stage == S) { stage = 0; phase ^= 1; }
       }
     }
-  } else if (warp == 1 && lane == 0 && leader) {
+  } else if (warp == 1 && leader) {
     // ============================== MMA issuer (leader CTA only) ==============================
     constexpr uint32_t idesc_full = make_idesc(BMT, BN, A_MN, B_MN);
     constexpr uint32_t idesc_half = make_idesc(BMT, BN / 2, A_MN, B_MN);
+    // descriptor halves (cute::UMMA::SmemDescriptor): lo = start address >> 4 | LBO >> 4 << 16, hi = SBO >> 4 | version
+    // | SWIZZLE_128B.  K-major: +32 B per 16-element k step inside the swizzled 128 B row (LBO unused, encoded 1);
+    // MN-major: +16 k-rows of 128 B per k step, LBO = BK * 128 B to the next 64-element mn box.
+    constexpr uint32_t kDescHi = (1024u >> 4) | (1u << 14) | (2u << 29);
+    constexpr uint32_t kLboA = (A_MN ? (uint32_t)(BK * 128) >> 4 : 1u) << 16, kStepA = A_MN ? (UMMA_K * 128) >> 4 : (UMMA_K * 2) >> 4;
+    constexpr uint32_t kLboB = (B_MN ? (uint32_t)(BK * 128) >> 4 : 1u) << 16, kStepB = B_MN ? (UMMA_K * 128) >> 4 : (UMMA_K * 2) >> 4;
+    const bool issuer = elect_one_sync();
     int stage = 0;
     uint32_t phase = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
-    Sched sched(stream_k, tiles_m, tiles_n, ragged, num_kb, worker, workers);
+    Sched sched(stream_k, tiles_m, tiles_n, ragged, num_kb, worker, workers, (dbg >> 3) & 1);
     Seg sg;
+    const uint32_t stage0 = smem_u32(stage_base);
     while (sched.next(sg)) {
       mbar_wait(&tempty[acc], acc_phase ^ 1);
       tc_fence_after();
@@ -351,21 +375,23 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       for (int kb = sg.kb0; kb < sg.kb1; ++kb) {
         if (!(dbg & 1)) mbar_wait(&full[stage], phase);
         tc_fence_after();
-        const uint32_t sa = smem_u32(stage_base + stage * Cfg::kStageBytes);
-        const uint32_t sb = sa + Cfg::kABytes;
+        const uint32_t sa = stage0 + stage * Cfg::kStageBytes;
+        const uint32_t la = ((sa >> 4) & 0x3FFFu) | kLboA;
+        const uint32_t lb = (((sa + Cfg::kABytes) >> 4) & 0x3FFFu) | kLboB;
+        if (issuer) {
 #pragma unroll
-        for (int k = 0; k < BK / UMMA_K; ++k) {
-          // K-major: +32 B inside the swizzled 128 B row per 16-element k step; MN-major: +16 k-rows of 128 B
-          const uint64_t da = A_MN ? make_smem_desc(sa + k * (UMMA_K * 128), BK * 128, 1024)
-                                   : make_smem_desc(sa + k * (UMMA_K * 2), 16, 1024);
-          const uint64_t db = B_MN ? make_smem_desc(sb + k * (UMMA_K * 128), BK * 128, 1024)
-                                   : make_smem_desc(sb + k * (UMMA_K * 2), 16, 1024);
-          if (!(dbg & 2)) umma_bf16<CG>(tmem_d, da, db, idesc, (kb > sg.kb0 || k > 0) ? 1u : 0u);
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            const uint64_t da = ((uint64_t)kDescHi << 32) | (la + k * kStepA);
+            const uint64_t db = ((uint64_t)kDescHi << 32) | (lb + k * kStepB);
+            if (!(dbg & 2)) umma_bf16<CG>(tmem_d, da, db, idesc, (kb > sg.kb0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit<CG>(&empty[stage]);
         }
-        umma_commit<CG>(&empty[stage]);
+        __syncwarp();
         if (++stage == S) { stage = 0; phase ^= 1; }
       }
-      umma_commit<CG>(&tfull[acc]);
+      if (issuer) umma_commit<CG>(&tfull[acc]);
+      __syncwarp();
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   } else if (warp >= 4) {
@@ -375,7 +401,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     float* st = staging + (warp - 4) * 32 * kStagePitch;
     int acc = 0;
     uint32_t acc_phase = 0;
-    Sched sched(stream_k, tiles_m, tiles_n, ragged, num_kb, worker, workers);
+    Sched sched(stream_k, tiles_m, tiles_n, ragged, num_kb, worker, workers, (dbg >> 3) & 1);
     Seg sg;
     while (sched.next(sg)) {
       const int m0 = (sg.tile / tiles_n) * BMT + (int)rank * BM, n0 = (sg.tile % tiles_n) * BN;
