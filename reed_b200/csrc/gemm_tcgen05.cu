@@ -100,14 +100,26 @@ static GemmPlan plan_gemm(int M, int N, int K, int b_mn, bool sk_ok, int force_c
         dp_cost = fmax(dp_cost, load);
       }
       double cost = dp_cost;
-      int sk = 0;
-      if (sk_ok && (int64_t)tiles * num_kb >= (int64_t)workers * 4) {
-        const double sk_cost = (double)tiles / workers * tile_cost + 3000.0;   // extra partial-tile epilogues
-        if (sk_cost < 0.93 * dp_cost) { cost = sk_cost; sk = 1; }
+      int sk = 0, grid = used * cg;
+      // split mode: whole rounds data-parallel, the tiles of the last partial round cut into k slices (one item per
+      // worker).  Worth it when that round would otherwise leave most of the machine idle.
+      const int full_rounds = tiles / workers, rem = tiles % workers;
+      if (sk_ok && rem > 0) {
+        int slices = workers / rem;
+        if (slices > num_kb / 2) slices = num_kb / 2;
+        if (slices >= 1) {
+          const double part = ceil_div(num_kb, slices) * per_kb + 1500.0 + (slices > 1 ? 2500.0 : 0.0);   // + red.add epilogue
+          const double sp_cost = full_rounds * tile_cost + part;
+          if (sp_cost < 0.95 * dp_cost) {
+            cost = sp_cost;
+            sk = slices;
+            grid = (full_rounds > 0 ? workers : rem * slices) * cg;
+          }
+        }
       }
       if (cost < best_cost) {
         best_cost = cost;
-        best = GemmPlan{cg, bn, sk, sk ? workers * cg : used * cg};
+        best = GemmPlan{cg, bn, sk, grid};
       }
     }
   }
@@ -124,8 +136,15 @@ int gemm_tcgen05(const void* A, int64_t lda, int a_mn, const void* B, int64_t ld
   // stream-K needs an output that tolerates fp32 atomics: no epilogue, no bias, fp32 D (the weight gradients)
   const bool sk_ok = ep.kind == kEpiNone && d_dtype == kF32 && ep.bias == nullptr && ep.out2 == nullptr;
   const GemmPlan p = plan_gemm(M, N, K, b_mn, sk_ok, g_force_cg, g_force_bn);
-  if (p.stream_k && !ep.accumulate)
-    REED_CHECK_CUDA(cudaMemset2DAsync(D, (size_t)ldd * 4, 0, (size_t)N * 4, (size_t)M, st));
+  if (p.stream_k > 1 && !ep.accumulate) {
+    // the sliced tiles are the last `rem` of the row-major tile order: zero the output from their first row panel on
+    // (whole-round tiles in that range overwrite it with plain stores afterwards - same stream, same kernel order)
+    const int workers = sm_count() / p.cg, tiles_n = ceil_div(N, p.bn), tiles = ceil_div(M, 128 * p.cg) * tiles_n;
+    const int first = (tiles / workers) * workers;
+    const int row0 = (first / tiles_n) * 128 * p.cg;
+    if (row0 < M)
+      REED_CHECK_CUDA(cudaMemset2DAsync((char*)D + (size_t)row0 * ldd * 4, (size_t)ldd * 4, 0, (size_t)N * 4, (size_t)(M - row0), st));
+  }
 
   CUtensorMap ma, mb;
   // K-major operand [MN, K] row-major: box = (128 | BN/CG) rows x 64 k.  MN-major operand stored [K, MN]: box = 64 k-rows x 64 mn.

@@ -3,7 +3,7 @@
 //   warp 0    : TMA producer          (one elected lane)
 //   warp 1    : tcgen05.mma issuer    (one elected lane), commits free smem stages / publish accumulators
 //   warp 2    : TMEM allocator
-//   warps 4-11: epilogue - tcgen05.ld the 128 x BN accumulator, transpose through smem so global accesses are
+//   warps 3-10: epilogue - tcgen05.ld the 128 x BN accumulator, transpose through smem so global accesses are
 //               row-coalesced, apply the fused epilogue (bias / GELU / SiLU / gate*y+residual / act') and store.
 // Two accumulator stages in TMEM let the epilogue of tile i overlap the MMAs of tile i+1.
 //
@@ -28,7 +28,8 @@ namespace reed {
 
 constexpr int BM = 128;         // accumulator rows per CTA (UMMA M = 128 x CG)
 constexpr int BK = 64;          // 64 bf16 = 128 B = one swizzle row
-constexpr int kGemmThreads = 384;   // warps 0-3: TMA / MMA / TMEM alloc / spare; warps 4-11: epilogue
+constexpr int kGemmThreads = 352;   // warps 0-2: TMA / MMA / TMEM alloc; warps 3-10: epilogue (184 registers per thread)
+constexpr int kFirstEpiWarp = 3;
 constexpr int kEpiWarps = 8;
 constexpr int kStageCols = 32;  // accumulator columns moved per tcgen05.ld
 constexpr int kStagePitch = 36; // floats; 144 B row pitch keeps float4 smem accesses conflict-free
@@ -54,52 +55,61 @@ struct GemmCfg {
   static constexpr int kTmemCols = 2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512);
 };
 
-// Work distribution.  Data-parallel: output tiles round-robin over the persistent CTAs.  Stream-K (fp32 accumulating
-// outputs, i.e. the weight-gradient GEMMs whose tile count does not fill 148 SMs evenly): the (tile, k-block) units
-// are cut into gridDim.x equal contiguous ranges; a CTA reduces each piece of a tile it owns in TMEM and adds it
-// into the zero-initialised (or accumulating) fp32 output with vector red.global.add.
-struct Seg { int tile, kb0, kb1, half; };   // half: the tile is the ragged last column tile, computed BN/2 wide
+// Work distribution.  Data-parallel: output tiles round-robin over the persistent CTAs (pairs), rounds in lock step,
+// so the CTAs running at any moment read the same k range of neighbouring tiles and L2 serves each operand line to
+// several SMs at once.  Split mode (fp32 outputs that tolerate atomics, i.e. the weight-gradient GEMMs, whose tile
+// count does not fill the machine evenly): the whole rounds run data-parallel with plain stores; the tiles of the
+// last, partial round are cut into `slices` equal k ranges, one (tile, slice) item per worker, neighbouring workers
+// on neighbouring tiles of the SAME slice, and added into the zeroed / accumulating output with red.global.add.
+// (A contiguous stream-K split gave every worker its own k phase: no two SMs wanted the same line at the same
+// time and the operand fetch fell back to the L2 data-array rate.)
+struct Seg { int tile, kb0, kb1, half, atomic; };   // half: the tile is the ragged last column tile, computed BN/2 wide
 struct Sched {
-  int sk, num_tiles, num_kb, tiles_n, ragged, round;
-  int64_t u, u_end;
-  int worker, stride, colmajor;
+  int slices, num_tiles, num_kb, tiles_n, ragged, round;
+  int worker, stride, colmajor, rem_done;
   // `worker` = index of this CTA (CG = 1) or CTA pair (CG = 2) among `workers`.
   // Data-parallel order: all full-width tiles first (row-major), then the ragged last-column tiles (when N leaves a
   // remainder of at most BN/2 they are computed with a BN/2-wide MMA and cost half a tile); rounds alternate
   // direction over the workers (snake), so the half tiles of the last rounds land on the workers that got one
   // tile less - e.g. N = 1152, BN = 256, M = 8192: 128 full + 32 half tiles on 74 pairs take 2 tile times, not 3.
-  __device__ Sched(int sk_, int tiles_m, int tiles_n_, int ragged_, int num_kb_, int worker_, int workers, int colmajor_ = 0)
-      : sk(sk_), num_tiles(tiles_m * tiles_n_), num_kb(num_kb_), tiles_n(tiles_n_), ragged(ragged_), round(0),
-        worker(worker_), stride(workers), colmajor(colmajor_) {
-    const int64_t total = (int64_t)num_tiles * num_kb;
-    u = total * worker / workers;
-    u_end = total * (worker + 1) / workers;
-  }
+  __device__ Sched(int slices_, int tiles_m, int tiles_n_, int ragged_, int num_kb_, int worker_, int workers, int colmajor_ = 0)
+      : slices(slices_), num_tiles(tiles_m * tiles_n_), num_kb(num_kb_), tiles_n(tiles_n_), ragged(ragged_), round(0),
+        worker(worker_), stride(workers), colmajor(colmajor_), rem_done(0) {}
   __device__ bool next(Seg& s) {
-    if (!sk) {
+    s.atomic = 0;
+    if (slices == 0) {
       const int v = round * stride + ((round & 1) ? stride - 1 - worker : worker);
       if (v >= num_tiles) return false;
       ++round;
+      s.kb0 = 0; s.kb1 = num_kb;
       if (colmajor) {   // profiling knob: walk the tiles down the columns (ragged handling off)
         const int tm = num_tiles / tiles_n;
-        s.tile = (v % tm) * tiles_n + v / tm; s.half = 0; s.kb0 = 0; s.kb1 = num_kb;
+        s.tile = (v % tm) * tiles_n + v / tm; s.half = 0;
         return true;
       }
       const int n_full = tiles_n - ragged;
       const int count_full = (num_tiles / tiles_n) * n_full;
       if (v < count_full) { s.tile = (v / n_full) * tiles_n + (v % n_full); s.half = 0; }
       else { s.tile = (v - count_full) * tiles_n + tiles_n - 1; s.half = 1; }
+      return true;
+    }
+    s.half = 0;
+    const int full_rounds = num_tiles / stride;
+    if (round < full_rounds) {
+      s.tile = round * stride + ((round & 1) ? stride - 1 - worker : worker);
+      ++round;
       s.kb0 = 0; s.kb1 = num_kb;
       return true;
     }
-    if (u >= u_end) return false;
-    const int t = (int)(u / num_kb);
-    const int kb0 = (int)(u - (int64_t)t * num_kb);
-    const int64_t left = u_end - u;
-    const int len = (num_kb - kb0) < left ? (num_kb - kb0) : (int)left;
-    s.tile = t; s.kb0 = kb0; s.kb1 = kb0 + len; s.half = 0;
-    u += len;
-    return true;
+    const int rem = num_tiles - full_rounds * stride;
+    if (rem_done || worker >= rem * slices) return false;
+    rem_done = 1;
+    const int sl = worker / rem;
+    s.tile = full_rounds * stride + worker % rem;
+    s.kb0 = (int)((int64_t)num_kb * sl / slices);
+    s.kb1 = (int)((int64_t)num_kb * (sl + 1) / slices);
+    s.atomic = slices > 1;
+    return s.kb1 > s.kb0;
   }
 };
 
@@ -240,6 +250,7 @@ template <int CG, int BN, int A_MN, int B_MN, typename TD>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                     TD* __restrict__ D, int64_t ldd, int M, int N, int K, EpiParams ep, int stream_k, int dbg) {
+  // stream_k: 0 = data-parallel; n >= 1 = split mode with n k-slices for the tiles of the last partial round
   // dbg (profiling only, results are garbage): 1 = no TMA (MMA does not wait for operands), 2 = no MMA issue,
   // 4 = no epilogue work (accumulators released immediately); 8 = column-major tile order (results stay correct)
   using Cfg = GemmCfg<CG, BN>;
@@ -394,11 +405,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       __syncwarp();
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
-  } else if (warp >= 4) {
+  } else if (warp >= kFirstEpiWarp) {
     // ============================== epilogue (8 warps per CTA, this CTA's 128 accumulator rows) ==============================
     const int q = warp & 3;                      // TMEM lane quadrant this warp may access
-    const int half = (warp - 4) >> 2;            // which 32-column chunks (even / odd) this warp drains
-    float* st = staging + (warp - 4) * 32 * kStagePitch;
+    const int half = (warp - kFirstEpiWarp) >> 2;            // which 32-column chunks (even / odd) this warp drains
+    float* st = staging + (warp - kFirstEpiWarp) * 32 * kStagePitch;
     int acc = 0;
     uint32_t acc_phase = 0;
     Sched sched(stream_k, tiles_m, tiles_n, ragged, num_kb, worker, workers, (dbg >> 3) & 1);
@@ -410,7 +421,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       if (dbg & 4) {
         mbar_wait(&tfull[acc], acc_phase);
       } else if constexpr (sizeof(TD) == 4) {
-        if (stream_k) REED_EPI(kEpiAtomic);
+        if (sg.atomic) REED_EPI(kEpiAtomic);
         else if (ep.kind == kEpiGateRes) REED_EPI(kEpiGateRes);
         else if (ep.kind == kEpiNone && ep.accumulate) REED_EPI(kEpiAccum);
         else if (ep.kind == kEpiNone) REED_EPI(kEpiNone);
