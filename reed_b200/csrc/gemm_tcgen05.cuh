@@ -193,56 +193,82 @@ __device__ __forceinline__ void epilogue_tile(const EpiParams& ep, TD* __restric
         *reinterpret_cast<float4*>(st + lane * kStagePitch + j * 4) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
     }
     __syncwarp();
-    // ... and pick them up row-coalesced: 8 lanes cover one 32-column row segment, 4 rows per instruction
+    // ... and pick them up row-coalesced: 8 lanes cover one 32-column row segment, 4 rows per instruction.
+    // All eight shared-memory reads are issued as one batch, and a chunk that lies fully inside the matrix (the
+    // common case, warp-uniform) runs without per-row predicates: with a branch per row the compiler serialises
+    // LDS -> use eight times over.
     const int col = n0 + c0 + cc;
-    const bool col_ok = col < N;
+    float4 fr[8];
 #pragma unroll
-    for (int it = 0; it < 8; ++it) {
-      const int r = it * 4 + rsub;
-      const int row = row_base + r;
-      const float4 f = *reinterpret_cast<const float4*>(st + r * kStagePitch + cc);
-      if (row < M && col_ok) {
-        F4 acc{{f.x + b4.x, f.y + b4.y, f.z + b4.z, f.w + b4.w}};
-        TD* dptr = D + (int64_t)row * ldd + col;
-        if constexpr (KIND == kEpiNone) {
-          store4(dptr, acc);
-        } else if constexpr (KIND == kEpiAccum) {
-          const float4 o = af[it];
-          acc.v[0] += o.x; acc.v[1] += o.y; acc.v[2] += o.z; acc.v[3] += o.w;
-          store4(dptr, acc);
-        } else if constexpr (KIND == kEpiAtomic) {
-          red_add4(reinterpret_cast<float*>(dptr), acc);
-        } else if constexpr (KIND == kEpiGelu || KIND == kEpiSilu) {
-          if (ep.out2) store4(reinterpret_cast<bf16*>(ep.out2) + (int64_t)row * ep.ld_out2 + col, acc);
-          F4 o;
+    for (int it = 0; it < 8; ++it) fr[it] = *reinterpret_cast<const float4*>(st + (it * 4 + rsub) * kStagePitch + cc);
+    const bool full = row_base + 32 <= M && n0 + c0 + kStageCols <= N;
+    auto row_op = [&](int it) {
+      const int row = row_base + it * 4 + rsub;
+      const float4 f = fr[it];
+      F4 acc{{f.x + b4.x, f.y + b4.y, f.z + b4.z, f.w + b4.w}};
+      TD* dptr = D + (int64_t)row * ldd + col;
+      if constexpr (KIND == kEpiNone) {
+        store4(dptr, acc);
+      } else if constexpr (KIND == kEpiAccum) {
+        const float4 o = af[it];
+        acc.v[0] += o.x; acc.v[1] += o.y; acc.v[2] += o.z; acc.v[3] += o.w;
+        store4(dptr, acc);
+      } else if constexpr (KIND == kEpiAtomic) {
+        red_add4(reinterpret_cast<float*>(dptr), acc);
+      } else if constexpr (KIND == kEpiGelu || KIND == kEpiSilu) {
+        if (ep.out2) store4(reinterpret_cast<bf16*>(ep.out2) + (int64_t)row * ep.ld_out2 + col, acc);
+        F4 o;
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const float h = round_bf16(acc.v[i]);   // activate the value backward will see
-            o.v[i] = KIND == kEpiGelu ? gelu_fast(h) : silu_fast(h);
-          }
-          store4(dptr, o);
-        } else if constexpr (KIND == kEpiGateRes) {
-          if (ep.out2) store4(reinterpret_cast<bf16*>(ep.out2) + (int64_t)row * ep.ld_out2 + col, acc);
-          const float4 rs = af[it];
-          float4 g = g4;
-          if (!g_uniform) g = __ldg(reinterpret_cast<const float4*>(ep.gate + (int64_t)(row / ep.rows_per_group) * ep.ld_gate + col));
-          F4 o{{rs.x + g.x * round_bf16(acc.v[0]), rs.y + g.y * round_bf16(acc.v[1]), rs.z + g.z * round_bf16(acc.v[2]),
-                rs.w + g.w * round_bf16(acc.v[3])}};
-          store4(dptr, o);
-        } else {   // kEpiDGelu / kEpiDSilu
-          const uint2 hv = ah[it];
-          const __nv_bfloat162 h01 = *reinterpret_cast<const __nv_bfloat162*>(&hv.x);
-          const __nv_bfloat162 h23 = *reinterpret_cast<const __nv_bfloat162*>(&hv.y);
-          const float h[4] = {__low2float(h01), __high2float(h01), __low2float(h23), __high2float(h23)};
-          F4 o;
-#pragma unroll
-          for (int i = 0; i < 4; ++i) o.v[i] = acc.v[i] * (KIND == kEpiDGelu ? gelu_grad_fast(h[i]) : silu_grad_fast(h[i]));
-          store4(dptr, o);
+        for (int i = 0; i < 4; ++i) {
+          const float h = round_bf16(acc.v[i]);   // activate the value backward will see
+          o.v[i] = KIND == kEpiGelu ? gelu_fast(h) : silu_fast(h);
         }
+        store4(dptr, o);
+      } else if constexpr (KIND == kEpiGateRes) {
+        if (ep.out2) store4(reinterpret_cast<bf16*>(ep.out2) + (int64_t)row * ep.ld_out2 + col, acc);
+        const float4 rs = af[it];
+        float4 g = g4;
+        if (!g_uniform) g = __ldg(reinterpret_cast<const float4*>(ep.gate + (int64_t)(row / ep.rows_per_group) * ep.ld_gate + col));
+        F4 o{{rs.x + g.x * round_bf16(acc.v[0]), rs.y + g.y * round_bf16(acc.v[1]), rs.z + g.z * round_bf16(acc.v[2]),
+              rs.w + g.w * round_bf16(acc.v[3])}};
+        store4(dptr, o);
+      } else {   // kEpiDGelu / kEpiDSilu
+        const uint2 hv = ah[it];
+        const __nv_bfloat162 h01 = *reinterpret_cast<const __nv_bfloat162*>(&hv.x);
+        const __nv_bfloat162 h23 = *reinterpret_cast<const __nv_bfloat162*>(&hv.y);
+        const float h[4] = {__low2float(h01), __high2float(h01), __low2float(h23), __high2float(h23)};
+        F4 o;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) o.v[i] = acc.v[i] * (KIND == kEpiDGelu ? gelu_grad_fast(h[i]) : silu_grad_fast(h[i]));
+        store4(dptr, o);
       }
+    };
+    if (full) {
+#pragma unroll
+      for (int it = 0; it < 8; ++it) row_op(it);
+    } else if (col < N) {
+#pragma unroll
+      for (int it = 0; it < 8; ++it)
+        if (row_base + it * 4 + rsub < M) row_op(it);
     }
     __syncwarp();
     if (ci + 2 < NCH && n0 + c0 + 2 * kStageCols < N) prefetch(c0 + 2 * kStageCols);
+  }
+}
+
+// The epilogue's global operand of a tile (residual stream / saved pre-activation / old D rows): pulled into L2 one
+// tile ahead by the warp that will consume it (lane = row, one 32-column segment per chunk), so the register
+// prefetch inside epilogue_tile pays an L2 hit instead of an HBM round trip per chunk.
+template <int BN>
+__device__ __forceinline__ void epilogue_l2_prefetch(const char* aux, int64_t pitch_bytes, int esz, int M, int N, int m0,
+                                                     int n0, int q, int half, int lane) {
+  const int row = m0 + q * 32 + lane;
+  if (aux == nullptr || row >= M) return;
+  const char* rp = aux + (int64_t)row * pitch_bytes;
+#pragma unroll
+  for (int ci = half; ci < BN / kStageCols; ci += 2) {
+    const int col = n0 + ci * kStageCols;
+    if (col < N) asm volatile("prefetch.global.L2 [%0];" ::"l"(rp + (int64_t)col * esz));
   }
 }
 
@@ -413,8 +439,21 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     int acc = 0;
     uint32_t acc_phase = 0;
     Sched sched(stream_k, tiles_m, tiles_n, ragged, num_kb, worker, workers, (dbg >> 3) & 1);
-    Seg sg;
-    while (sched.next(sg)) {
+    // global operand of the fused epilogue, if any (see epilogue_l2_prefetch)
+    const char* aux = nullptr;
+    int64_t aux_pitch = 0;
+    int aux_esz = 4;
+    if (ep.kind == kEpiGateRes) { aux = (const char*)ep.aux; aux_pitch = ep.ld_aux * 4; }
+    else if (ep.kind == kEpiDGelu || ep.kind == kEpiDSilu) { aux = (const char*)ep.aux; aux_pitch = ep.ld_aux * 2; aux_esz = 2; }
+    else if (ep.kind == kEpiNone && ep.accumulate && sizeof(TD) == 4) { aux = (const char*)D; aux_pitch = ldd * 4; }
+    Seg sg, nx;
+    bool have = sched.next(sg);
+    if (have && !sg.atomic)
+      epilogue_l2_prefetch<BN>(aux, aux_pitch, aux_esz, M, N, (sg.tile / tiles_n) * BMT + (int)rank * BM, (sg.tile % tiles_n) * BN, q, half, lane);
+    while (have) {
+      const bool have_next = sched.next(nx);
+      if (have_next && !nx.atomic)
+        epilogue_l2_prefetch<BN>(aux, aux_pitch, aux_esz, M, N, (nx.tile / tiles_n) * BMT + (int)rank * BM, (nx.tile % tiles_n) * BN, q, half, lane);
       const int m0 = (sg.tile / tiles_n) * BMT + (int)rank * BM, n0 = (sg.tile % tiles_n) * BN;
       const uint32_t taddr = tmem_base + acc * BN + ((uint32_t)(q * 32) << 16);
 #define REED_EPI(KIND) epilogue_tile<KIND, BN, TD>(ep, D, ldd, M, N, m0, n0, taddr, st, q, half, lane, &tfull[acc], acc_phase)
@@ -444,6 +483,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         else mbar_arrive_cluster(mapa_u32(smem_u32(&tempty[acc]), 0));
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      sg = nx;
+      have = have_next;
     }
   }
   tc_fence_before();
