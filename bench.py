@@ -165,7 +165,7 @@ def build_trainer(cfg, dev, precision="bf16"):
                 p.copy_(torch.randn(p.shape, generator=g) * 0.02)
     model = model.to(dev).train()
     loss_fn = SILoss(enc_names=cfg["enc_names"], loss_weights=cfg["loss_weights"])
-    return ReedTrainer(model, loss_fn, precision=precision), spec
+    return ReedTrainer(model, loss_fn, precision=precision, comm_sms=int(os.environ.get("REED_COMM_SMS", "16"))), spec
 
 
 def make_batches(cfg, spec, dev, n_buf):
@@ -192,6 +192,8 @@ def run_gpu_arm(args, cfg):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        # the all-reduce kernels share the GPU with the backward GEMMs: cap their CTAs to the SMs the trainer reserves
+        os.environ.setdefault("NCCL_MAX_CTAS", os.environ.get("REED_COMM_SMS", "16"))
         dist.init_process_group("nccl", device_id=dev)
     _cabi.load()
     ops.device_check()

@@ -28,6 +28,10 @@ int reed_version(void);
 const char* reed_last_error(void);
 /* 0 iff the current CUDA device is an sm_100 part; copies its name into `name` when non-NULL. */
 int reed_device_check(char* name, int name_len);
+/* Number of SMs the persistent tensor-core GEMM grids leave free from now on (0 = none).  The data-parallel trainer
+ * sets it around backward so the overlapped NCCL gradient all-reduce (train.py:151,293,401 - accelerate/DDP) finds
+ * SMs without splitting a GEMM grid into two waves.  Host-side state, not a stream operation. */
+int reed_gemm_reserve_sms(int n);
 
 /* D[M,N] = epilogue(A[M,K] . B[N,K]^T)   -- every nn.Linear of the model and its dgrad/wgrad.
  * Replaces: timm Attention.qkv/.proj and Mlp.fc1/.fc2 (models/sit.py:114-124,134-135), adaLN linears (125-133,

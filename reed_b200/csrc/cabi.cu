@@ -22,6 +22,7 @@ int gemm_tcgen05(const void* A, int64_t lda, int a_mn, const void* B, int64_t ld
 bool gemm_tcgen05_supported(int64_t lda, int64_t ldb, int64_t ldd, const void* A, const void* B, int M, int N, int K);
 void gemm_tcgen05_force_cta_group(int cg);
 void gemm_tcgen05_force_bn(int bn);
+void gemm_tcgen05_reserve_sms(int n);
 int attn_simt_fwd(int act_dtype, const void* qkv, void* o, float* lse, int B, int T, int H, int hd, cudaStream_t st);
 int attn_simt_bwd(int act_dtype, const void* qkv, const void* o, const void* d_o, const float* lse, void* dqkv,
                   float* delta, int B, int T, int H, int hd, cudaStream_t st);
@@ -50,6 +51,15 @@ extern "C" int reed_device_check(char* name, int name_len) {
   REED_CHECK_CUDA(cudaGetDeviceProperties(&prop, dev));
   if (name && name_len > 0) snprintf(name, name_len, "%s", prop.name);
   REED_REQUIRE(prop.major == 10, "libreed_sm100 needs an sm_100 device, found sm_%d%d (%s)", prop.major, prop.minor, prop.name);
+  return 0;
+}
+
+// SMs the persistent tensor-core GEMM grids leave free from now on (host-side planner state; 0 = use every SM).
+// The data-parallel trainer raises it around backward so the NCCL all-reduce kernels of finished gradient buckets
+// find SMs without pushing part of a GEMM grid into a second wave (train.py:401: DDP's overlapped all-reduce).
+extern "C" int reed_gemm_reserve_sms(int n) {
+  REED_REQUIRE(n >= 0 && n <= 64, "gemm_reserve_sms: %d out of range", n);
+  gemm_tcgen05_reserve_sms(n);
   return 0;
 }
 

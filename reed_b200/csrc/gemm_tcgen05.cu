@@ -1,5 +1,6 @@
 // Host side of the tcgen05 GEMM: tensor maps, tile/cluster/stream-K plan, dispatch to the cta_group::1 / ::2 kernels.
 #include <cuda.h>
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace reed {
@@ -46,6 +47,12 @@ bool gemm_tcgen05_supported(int64_t lda, int64_t ldb, int64_t ldd, const void* A
          M >= 1 && N >= 16 && K >= 16;   // K < 64: TMA zero-fills the rest of the 64-wide k-block
 }
 
+// SMs the persistent GEMM grids leave free (reed_gemm_reserve_sms): under data parallelism the NCCL all-reduce
+// kernels of finished buckets run beside the backward GEMMs; a 148-CTA persistent grid that finds some SMs taken
+// runs its last CTAs as a second wave and nearly doubles in time.
+static int g_reserve_sms = -1;
+void gemm_tcgen05_reserve_sms(int n) { g_reserve_sms = n < 0 ? 0 : n; }
+
 static int sm_count() {
   static int n = 0;
   if (n == 0) {
@@ -53,7 +60,10 @@ static int sm_count() {
     cudaGetDevice(&dev);
     if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = kNumSMs;
   }
-  return n;
+  if (g_reserve_sms < 0) g_reserve_sms = getenv("REED_GEMM_RESERVE_SMS") ? atoi(getenv("REED_GEMM_RESERVE_SMS")) : 0;
+  int use = n - g_reserve_sms;
+  use -= use & 1;
+  return use < 2 ? 2 : use;
 }
 
 // Plan: cta_group (1 / 2), tile width BN, data-parallel or stream-K.  Cost model per k-block and per CTA, in SM

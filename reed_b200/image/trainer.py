@@ -183,7 +183,7 @@ class ReedTrainer:
 
     def __init__(self, model: nn.Module, loss_fn, *, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0,
                  max_grad_norm=1.0, ema_decay=0.9999, proj_coeff=0.5, precision: Optional[str] = "bf16", group=None,
-                 with_ema=True):
+                 with_ema=True, comm_sms: int = 16):
         self.model = model
         self.loss_fn = loss_fn
         self.lr, self.betas, self.eps, self.weight_decay = lr, betas, eps, weight_decay
@@ -198,6 +198,8 @@ class ReedTrainer:
             self.ema.eval()
         self.state = FlatState(model, self.ema, with_shadow=True)
         self.reducer = GradientReducer(self.state, group)
+        # SMs left to the NCCL kernels while backward overlaps the bucket all-reduces (bench.py caps NCCL's CTAs to match)
+        self.comm_sms = comm_sms if self.reducer.world > 1 else 0
         if self.reducer.world > 1:                      # DDP broadcasts rank 0's weights when it wraps the model
             for b in self.state.buckets:
                 dist.broadcast(b.param, 0, group=group)
@@ -244,6 +246,18 @@ class ReedTrainer:
             if ep is not None:
                 ops._launch("reed_ema_update", p.data_ptr(), ep.data_ptr(), p.numel(), self.ema_decay, st)
 
+    def _backward(self, loss):
+        """backward with the per-bucket all-reduces in flight; the GEMM grids shrink by comm_sms SMs meanwhile."""
+        if self.comm_sms:
+            ops.call("reed_gemm_reserve_sms", self.comm_sms)
+        try:
+            loss.backward()
+            self.state.finish_backward()
+            self.reducer.finish()
+        finally:
+            if self.comm_sms:
+                ops.call("reed_gemm_reserve_sms", 0)
+
     def grad_norm(self) -> torch.Tensor:
         """Global gradient norm of the last step (device scalar, after the all-reduce average)."""
         return (self._norm_sq.sqrt() * self.reducer.grad_scale).float()
@@ -251,9 +265,7 @@ class ReedTrainer:
     def train_step(self, images, labels, zs, diffusion_decay=1.0, repa_decay=1.0):
         self.state.begin_step()
         loss, out = self.compute_loss(images, labels, zs, diffusion_decay, repa_decay)
-        loss.backward()
-        self.state.finish_backward()
-        self.reducer.finish()
+        self._backward(loss)
         self.optimizer_step()
         return loss.detach(), out
 
@@ -267,9 +279,7 @@ class ReedTrainer:
         self.state.begin_step()
         loss, out = self.compute_loss(g["images"], g["labels"], g["zs"], g["scalars"][0], g["scalars"][1],
                                       time_input=g["time"])
-        loss.backward()
-        self.state.finish_backward()
-        self.reducer.finish()
+        self._backward(loss)
         self.optimizer_step(device_step=True)
         return loss.detach(), out
 
