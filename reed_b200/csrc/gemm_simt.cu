@@ -84,48 +84,86 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const TA* __restrict__ A
 // whose contraction is the batch).  An outer-product stream: 2 small operand tiles in shared memory, every thread
 // owns a 4 x 4 output block, rows written as coalesced float4 - bounded by the HBM write of N*K floats.
 // ------------------------------------------------------------------------------------------------
-constexpr int kOwN = 32, kOwK = 128;
+constexpr int kOwN = 64, kOwK = 128;
 
+// CTA = 64 x 128 outputs, thread = 8 rows x 4 columns; the batch rows of dy / x are staged in shared memory as fp32.
+// Row pairs ride on the packed fp32 FMA (FFMA2): 16 issue slots per batch row for 32 FMAs, operands from three
+// LDS.128 (the dy values are a warp-wide broadcast).  The kernel is bound by its M*N fp32 writes.
 template <typename TA>
 __global__ void __launch_bounds__(256) outer_wgrad_kernel(const TA* __restrict__ dy, int64_t ld_dy, const TA* __restrict__ x,
                                                            int64_t ld_x, float* __restrict__ D, int64_t ldd, int N, int K,
                                                            int B, int accumulate) {
-  __shared__ float sdy[64][kOwN];
-  __shared__ float sx[64][kOwK];
+  __shared__ __align__(16) float sdy[64][kOwN];
+  __shared__ __align__(16) float sx[64][kOwK];
   const int tid = threadIdx.x;
   const int n0 = blockIdx.y * kOwN, k0 = blockIdx.x * kOwK;
-  for (int e = tid; e < B * kOwN; e += 256) {
-    const int b = e / kOwN, n = e % kOwN;
-    sdy[b][n] = (n0 + n < N) ? to_f(dy[(int64_t)b * ld_dy + n0 + n]) : 0.f;
-  }
-  for (int e = tid; e < B * kOwK; e += 256) {
-    const int b = e / kOwK, k = e % kOwK;
-    sx[b][k] = (k0 + k < K) ? to_f(x[(int64_t)b * ld_x + k0 + k]) : 0.f;
+  constexpr bool kBf = sizeof(TA) == 2;
+  const bool fast = kBf && n0 + kOwN <= N && k0 + kOwK <= K && ld_dy % 8 == 0 && ld_x % 8 == 0 &&
+                    (((uintptr_t)dy | (uintptr_t)x) & 15) == 0;
+  if (fast) {
+    // 8 bf16 per 16-byte load
+    for (int e = tid; e < B * (kOwN / 8); e += 256) {
+      const int b = e / (kOwN / 8), c = e % (kOwN / 8);
+      const uint4 v = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(dy) + (int64_t)b * ld_dy + n0 + c * 8));
+      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        sdy[b][c * 8 + 2 * i] = __low2float(h[i]);
+        sdy[b][c * 8 + 2 * i + 1] = __high2float(h[i]);
+      }
+    }
+    for (int e = tid; e < B * (kOwK / 8); e += 256) {
+      const int b = e / (kOwK / 8), c = e % (kOwK / 8);
+      const uint4 v = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(x) + (int64_t)b * ld_x + k0 + c * 8));
+      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        sx[b][c * 8 + 2 * i] = __low2float(h[i]);
+        sx[b][c * 8 + 2 * i + 1] = __high2float(h[i]);
+      }
+    }
+  } else {
+    for (int e = tid; e < B * kOwN; e += 256) {
+      const int b = e / kOwN, n = e % kOwN;
+      sdy[b][n] = (n0 + n < N) ? to_f(dy[(int64_t)b * ld_dy + n0 + n]) : 0.f;
+    }
+    for (int e = tid; e < B * kOwK; e += 256) {
+      const int b = e / kOwK, k = e % kOwK;
+      sx[b][k] = (k0 + k < K) ? to_f(x[(int64_t)b * ld_x + k0 + k]) : 0.f;
+    }
   }
   __syncthreads();
-  const int tk = (tid & 31) * 4, tn = (tid >> 5) * 4;
-  float acc[4][4];
+  const int tk = (tid & 31) * 4, tn = (tid >> 5) * 8;
+  float2 acc[4][4];   // [row pair][column]: (row 2p, row 2p+1)
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int p = 0; p < 4; ++p)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    for (int j = 0; j < 4; ++j) acc[p][j] = make_float2(0.f, 0.f);
+#pragma unroll 4
   for (int b = 0; b < B; ++b) {
-    const float4 a4 = *reinterpret_cast<const float4*>(&sdy[b][tn]);     // same address across the warp: broadcast
+    const float4 a0 = *reinterpret_cast<const float4*>(&sdy[b][tn]);     // same address across the warp: broadcast
+    const float4 a1 = *reinterpret_cast<const float4*>(&sdy[b][tn + 4]);
     const float4 x4 = *reinterpret_cast<const float4*>(&sx[b][tk]);
-    const float a[4] = {a4.x, a4.y, a4.z, a4.w}, xv[4] = {x4.x, x4.y, x4.z, x4.w};
+    const float2 ap[4] = {make_float2(a0.x, a0.y), make_float2(a0.z, a0.w), make_float2(a1.x, a1.y), make_float2(a1.z, a1.w)};
+    const float xv[4] = {x4.x, x4.y, x4.z, x4.w};
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int j = 0; j < 4; ++j) {
+      const float2 xx = make_float2(xv[j], xv[j]);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], xv[j], acc[i][j]);
+      for (int p = 0; p < 4; ++p) acc[p][j] = __ffma2_rn(ap[p], xx, acc[p][j]);
+    }
   }
   const int col = k0 + tk;
   if (col >= K) return;
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
+  for (int i = 0; i < 8; ++i) {
     const int row = n0 + tn + i;
     if (row >= N) continue;
     float* d = D + (int64_t)row * ldd + col;
-    F4 o{{acc[i][0], acc[i][1], acc[i][2], acc[i][3]}};
+    const int p = i >> 1;
+    F4 o;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) o.v[j] = (i & 1) ? acc[p][j].y : acc[p][j].x;
     if (accumulate) {
       const F4 old = load4(d);
 #pragma unroll
