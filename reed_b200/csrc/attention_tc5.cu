@@ -267,6 +267,7 @@ template <int HD>
 __global__ void __launch_bounds__(kFwdThreads, 1)
 attn_tc5_fwd_kernel(const __grid_constant__ AttnMaps maps, float* __restrict__ lse, int T, int H, int num_items,
                     float scale_log2) {
+  pdl_launch();   // dependents (the next GEMM of the stream) may start their prologue
   using TL = Tile<HD>;
   using SM = FwdSmem<HD>;
   extern __shared__ uint8_t smem_raw[];
@@ -492,6 +493,7 @@ template <int HD>
 __global__ void __launch_bounds__(kBwdThreads, 1)
 attn_tc5_dq_kernel(const __grid_constant__ AttnMaps maps, const float* __restrict__ lse, float* __restrict__ delta,
                    int T, int H, float scale, float scale_log2) {
+  pdl_launch();   // dependents (the next GEMM of the stream) may start their prologue
   using TL = Tile<HD>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -622,6 +624,7 @@ template <int HD>
 __global__ void __launch_bounds__(kBwdThreads, 1)
 attn_tc5_dkv_kernel(const __grid_constant__ AttnMaps maps, const float* __restrict__ lse, const float* __restrict__ delta,
                     int T, int H, float scale, float scale_log2) {
+  pdl_launch();   // dependents (the next GEMM of the stream) may start their prologue
   using TL = Tile<HD>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);

@@ -171,4 +171,12 @@ __device__ __forceinline__ void epilogue_store4(const EpiParams& ep, TD* __restr
 
 inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
+// Programmatic dependent launch (sm_90+).  pdl_launch(): this grid no longer holds back a dependent grid that was
+// launched with the programmatic-serialization attribute - its CTAs may become resident (and run their prologue) as
+// soon as SMs free up.  pdl_wait(): returns once every grid this one depends on has completed and its writes are
+// visible; a no-op for a grid launched without the attribute.  A kernel launched WITH the attribute must call
+// pdl_wait() before its first global-memory access.
+__device__ __forceinline__ void pdl_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 }  // namespace reed

@@ -60,6 +60,7 @@ __global__ void __launch_bounds__(kLnWarps * 32) ln_modulate_fwd_kernel(
     const float* __restrict__ x, const float* __restrict__ shift, const float* __restrict__ scale, int64_t ld_mod,
     int rows_per_group, int rows_per_cta, TA* __restrict__ out, float* __restrict__ mean_out,
     float* __restrict__ rstd_out, int M, int D, float eps) {
+  pdl_launch();   // dependents (the next GEMM of the stream) may start their prologue
   extern __shared__ __align__(128) uint8_t ln_smem[];
   __shared__ uint64_t bars[kLnWarps][kLnStages];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -201,6 +202,7 @@ __host__ __device__ inline int row_slot_bytes(int D, bool has_res) {
 
 template <typename TA, int V, bool LN, bool GATE>
 __global__ void __launch_bounds__(kRowMaxThreads) row_bwd_kernel(const RowBwdParams p) {
+  pdl_launch();   // dependents (the next GEMM of the stream) may start their prologue
   extern __shared__ __align__(128) uint8_t row_smem[];
   __shared__ uint64_t full[kRowStages];
   __shared__ float2 red[2][kRowMaxThreads / 32];
@@ -391,6 +393,7 @@ __global__ void __launch_bounds__(kRowMaxThreads) row_bwd_kernel(const RowBwdPar
 template <typename TA>
 __global__ void __launch_bounds__(256) colsum_kernel(const TA* __restrict__ src, int64_t ld, float* __restrict__ out,
                                                       int M, int N, int rows_per_cta) {
+  pdl_launch();   // dependents (the next GEMM of the stream) may start their prologue
   __shared__ float red[8][128];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int col = blockIdx.x * 128 + lane * 4;
@@ -423,6 +426,7 @@ enum UnaryOp { kCast = 0, kSilu = 1 };
 
 template <typename TI, typename TO, int OP>
 __global__ void __launch_bounds__(256) unary_kernel(const TI* __restrict__ in, TO* __restrict__ out, int64_t n4) {
+  pdl_launch();   // dependents (the next GEMM of the stream) may start their prologue
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
     F4 v = load4(in + i * 4);
     if (OP == kSilu) {

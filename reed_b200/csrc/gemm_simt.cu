@@ -93,6 +93,7 @@ template <typename TA>
 __global__ void __launch_bounds__(256) outer_wgrad_kernel(const TA* __restrict__ dy, int64_t ld_dy, const TA* __restrict__ x,
                                                            int64_t ld_x, float* __restrict__ D, int64_t ldd, int N, int K,
                                                            int B, int accumulate) {
+  pdl_launch();   // dependents (the next GEMM of the stream) may start their prologue
   __shared__ __align__(16) float sdy[64][kOwN];
   __shared__ __align__(16) float sx[64][kOwK];
   const int tid = threadIdx.x;

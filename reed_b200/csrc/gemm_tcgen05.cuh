@@ -326,6 +326,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   if constexpr (CG == 2) cluster_sync_all();   // the peer's barriers are initialised before anything signals them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // Everything above (barriers, TMEM, descriptor prefetch) touched no global data: under programmatic dependent launch
+  // it ran while the previous kernel of the stream was still draining.  From here on its results are needed.
+  pdl_launch();
+  pdl_wait();
 
   // The TMA and MMA warps run warp-uniform code: all 32 lanes walk the schedule and poll the barriers, one elected
   // lane executes the TMA / tcgen05 instructions.  Those take their operands from uniform registers; issued from a
@@ -515,13 +519,16 @@ static int launch(const CUtensorMap& ma, const CUtensorMap& mb, void* D, int64_t
   cfg.blockDim = dim3(kGemmThreads);
   cfg.dynamicSmemBytes = Cfg::kSmemBytes;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  static const int pdl = getenv("REED_PDL") ? atoi(getenv("REED_PDL")) : 1;
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CG;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = pdl ? 2 : 1;
   REED_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kernel, ma, mb, (TD*)D, ldd, M, N, K, ep, stream_k, dbg));
   return 0;
 }
