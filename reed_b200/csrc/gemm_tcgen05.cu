@@ -5,10 +5,14 @@
 
 namespace reed {
 
+struct EpiMaps { CUtensorMap d, o2, aux; };   // same layout as in gemm_tcgen05.cuh
+
 int gemm_tc_launch_cg1(int bn, int a_mn, int b_mn, const CUtensorMap& ma, const CUtensorMap& mb, void* D, int64_t ldd,
-                       int d_dtype, int M, int N, int K, const EpiParams& ep, cudaStream_t st, int grid, int stream_k);
+                       int d_dtype, int M, int N, int K, const EpiParams& ep, cudaStream_t st, int grid, int stream_k,
+                       const EpiMaps* em);
 int gemm_tc_launch_cg2(int bn, int a_mn, int b_mn, const CUtensorMap& ma, const CUtensorMap& mb, void* D, int64_t ldd,
-                       int d_dtype, int M, int N, int K, const EpiParams& ep, cudaStream_t st, int grid, int stream_k);
+                       int d_dtype, int M, int N, int K, const EpiParams& ep, cudaStream_t st, int grid, int stream_k,
+                       const EpiMaps* em);
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -41,6 +45,27 @@ static int make_map(CUtensorMap* map, const void* ptr, int64_t rows, int64_t col
                (long long)rows, (long long)cols, (long long)ld, box_rows);
   return 0;
 }
+
+// [32 rows x 32 columns] box over a row-major [rows, cols] matrix for the TMA epilogue: bf16 -> 64-byte rows with
+// SWIZZLE_64B, fp32 -> 128-byte rows with SWIZZLE_128B (one epilogue warp's share of a 32-column chunk)
+static int make_epi_map(CUtensorMap* map, const void* ptr, int dtype, int64_t rows, int64_t cols, int64_t ld) {
+  EncodeTiledFn enc = get_encode_fn();
+  REED_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled is not available from the driver");
+  const int esz = dtype == kF32 ? 4 : 2;
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * esz};
+  cuuint32_t box[2] = {32u, 32u};
+  cuuint32_t estr[2] = {1u, 1u};
+  CUresult r = enc(map, dtype == kF32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+                   const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   dtype == kF32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  REED_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled (epilogue box) failed (%d) rows=%lld cols=%lld ld=%lld", (int)r,
+               (long long)rows, (long long)cols, (long long)ld);
+  return 0;
+}
+
+static bool tma_ok_ptr(const void* p, int64_t ld, int esz) { return ((uintptr_t)p & 15) == 0 && (ld * esz) % 16 == 0; }
 
 bool gemm_tcgen05_supported(int64_t lda, int64_t ldb, int64_t ldd, const void* A, const void* B, int M, int N, int K) {
   return lda % 8 == 0 && ldb % 8 == 0 && ldd % 4 == 0 && N % 8 == 0 && (((uintptr_t)A | (uintptr_t)B) & 15) == 0 &&
@@ -160,8 +185,28 @@ int gemm_tcgen05(const void* A, int64_t lda, int a_mn, const void* B, int64_t ld
   // K-major operand [MN, K] row-major: box = (128 | BN/CG) rows x 64 k.  MN-major operand stored [K, MN]: box = 64 k-rows x 64 mn.
   if (a_mn) { if (make_map(&ma, A, K, M, lda, 64)) return 1; } else { if (make_map(&ma, A, M, K, lda, 128)) return 1; }
   if (b_mn) { if (make_map(&mb, B, K, N, ldb, 64)) return 1; } else { if (make_map(&mb, B, N, K, ldb, p.bn / p.cg)) return 1; }
-  if (p.cg == 2) return gemm_tc_launch_cg2(p.bn, a_mn, b_mn, ma, mb, D, ldd, d_dtype, M, N, K, ep, st, p.grid, p.stream_k);
-  return gemm_tc_launch_cg1(p.bn, a_mn, b_mn, ma, mb, D, ldd, d_dtype, M, N, K, ep, st, p.grid, p.stream_k);
+  // TMA epilogue (epilogue_loop_tma): bf16 D with none / activation / activation-gradient, fp32 D with gate+residual
+  static const int tma_epi_on = getenv("REED_TMA_EPI") ? atoi(getenv("REED_TMA_EPI")) : 7;
+  EpiMaps em;
+  const EpiMaps* emp = nullptr;
+  const bool act_kind = ep.kind == kEpiNone || ep.kind == kEpiGelu || ep.kind == kEpiSilu || ep.kind == kEpiDGelu || ep.kind == kEpiDSilu;
+  const bool want_o2 = ep.out2 != nullptr && (ep.kind == kEpiGelu || ep.kind == kEpiSilu || ep.kind == kEpiGateRes);
+  const bool has_aux = ep.kind == kEpiDGelu || ep.kind == kEpiDSilu || ep.kind == kEpiGateRes;
+  // REED_TMA_EPI: bit 0 = activation-gradient kinds (fused operand), bit 1 = activation kinds, bit 2 = plain bf16 stores
+  const int kind_bit = (ep.kind == kEpiDGelu || ep.kind == kEpiDSilu) ? 1 : ((ep.kind == kEpiGelu || ep.kind == kEpiSilu) ? 2 : 4);
+  bool tma = (tma_epi_on & kind_bit) && !p.stream_k && !ep.accumulate && d_dtype == kBF16 && act_kind &&
+             tma_ok_ptr(D, ldd, d_dtype == kF32 ? 4 : 2) && (!want_o2 || tma_ok_ptr(ep.out2, ep.ld_out2, 2)) &&
+             (!has_aux || tma_ok_ptr(ep.aux, ep.ld_aux, ep.kind == kEpiGateRes ? 4 : 2)) &&
+             (ep.bias == nullptr || ((uintptr_t)ep.bias & 15) == 0) &&
+             (ep.kind != kEpiGateRes || (((uintptr_t)ep.gate & 15) == 0 && ep.ld_gate % 4 == 0));
+  if (tma) {
+    if (make_epi_map(&em.d, D, d_dtype, M, N, ldd)) return 1;
+    if (want_o2) { if (make_epi_map(&em.o2, ep.out2, kBF16, M, N, ep.ld_out2)) return 1; } else em.o2 = em.d;
+    if (has_aux) { if (make_epi_map(&em.aux, ep.aux, ep.kind == kEpiGateRes ? kF32 : kBF16, M, N, ep.ld_aux)) return 1; } else em.aux = em.d;
+    emp = &em;
+  }
+  if (p.cg == 2) return gemm_tc_launch_cg2(p.bn, a_mn, b_mn, ma, mb, D, ldd, d_dtype, M, N, K, ep, st, p.grid, p.stream_k, emp);
+  return gemm_tc_launch_cg1(p.bn, a_mn, b_mn, ma, mb, D, ldd, d_dtype, M, N, K, ep, st, p.grid, p.stream_k, emp);
 }
 
 }  // namespace reed

@@ -43,17 +43,25 @@ struct GemmCfg {
   static constexpr int kABytes = BM * BK * 2;
   static constexpr int kBBytes = kBNL * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStagingBytes = kEpiWarps * 32 * kStagePitch * 4;
-  static constexpr int kBudget = 227 * 1024 - 1024 /*align slack*/ - kStagingBytes - 256 /*barriers*/;
-  static constexpr int kStagesFit = (kBudget / kStageBytes) > 8 ? 8 : (kBudget / kStageBytes);
+  static constexpr int kStagingBytes = kEpiWarps * 32 * kStagePitch * 4;   // epilogue region of the register/LSU epilogue
+  static constexpr int kTmaEpiBytes = kEpiWarps * 8192;                    // epilogue region of the TMA epilogue ...
+  static constexpr int kTmaEpiAuxBytes = kEpiWarps * 10240;                // ... with a fused global operand
+  static constexpr int kBarBytes = 512;
+  // shared memory = 1024 (alignment slack) + stages * kStageBytes + epilogue region + barriers
+  static constexpr int stages_for(int epi_bytes) {
+    int s = (227 * 1024 - 1024 - epi_bytes - kBarBytes) / kStageBytes;
 #ifdef REED_GEMM_MAX_STAGES
-  static constexpr int kStages = kStagesFit > REED_GEMM_MAX_STAGES ? REED_GEMM_MAX_STAGES : kStagesFit;
-#else
-  static constexpr int kStages = kStagesFit;
+    if (s > REED_GEMM_MAX_STAGES) s = REED_GEMM_MAX_STAGES;
 #endif
-  static constexpr int kSmemBytes = 1024 + kStages * kStageBytes + kStagingBytes + 256;
+    return s > 8 ? 8 : s;
+  }
+  static constexpr int smem_bytes(int stages, int epi_bytes) { return 1024 + stages * kStageBytes + epi_bytes + kBarBytes; }
   static constexpr int kTmemCols = 2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512);
 };
+
+// Tensor maps of the TMA epilogue: D, out2 (bf16) and the fused global operand, all as [32 rows x 32 columns] boxes
+// (one epilogue warp's share of a chunk) with the 64-byte (bf16) / 128-byte (fp32) swizzle.
+struct EpiMaps { CUtensorMap d, o2, aux; };
 
 // Work distribution.  Data-parallel: output tiles round-robin over the persistent CTAs (pairs), rounds in lock step,
 // so the CTAs running at any moment read the same k range of neighbouring tiles and L2 serves each operand line to
@@ -272,15 +280,213 @@ __device__ __forceinline__ void epilogue_l2_prefetch(const char* aux, int64_t pi
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// TMA epilogue.  Every epilogue warp is its own pipeline over its chunks (32 accumulator rows x 32 columns), with no
+// global loads or stores executed by its threads:
+//   * the fused global operand of a chunk (saved pre-activation, bf16 / residual stream, fp32) arrives in the warp's
+//     own shared-memory ring by TMA, requested 1-2 chunks ahead - across tile boundaries - and tracked by mbarriers,
+//     not by register scoreboards;
+//   * tcgen05.ld leaves thread = accumulator row; the math runs in that layout and reads the operand row from the
+//     swizzled box (conflict-free 16-byte accesses);
+//   * results are packed into a swizzled [32 x 32] box per output and written back by TMA stores (bulk groups; a box
+//     is reused once the store issued two chunks earlier has read it).  The residual box is updated in place.
+// bf16 outputs only (none / activation / activation-gradient).  Per-warp region: [operand slots x3][D boxes x2]
+// [out2 boxes x2] - 10 KB with a fused operand, 8 KB without.
+// ------------------------------------------------------------------------------------------------
+template <int KIND> struct TmaEpi {
+  static constexpr bool kAuxBf16 = KIND == kEpiDGelu || KIND == kEpiDSilu;
+  static constexpr bool kAuxF32 = false;                    // (the fp32 gate+residual epilogue stays on the register path)
+  static constexpr bool kOut2 = KIND == kEpiGelu || KIND == kEpiSilu;
+  static constexpr int kSlots = kAuxBf16 ? 3 : 0;
+  static constexpr int kLook = 2;                           // operand requests in flight ahead of the chunk in work
+  static_assert(kSlots == 0 || kSlots == kLook + 1, "a ring slot is reused by the request kLook + 1 chunks later");
+  static constexpr int kSlotBytes = kAuxBf16 ? 2048 : 4096;
+  static constexpr int kOutOff = kSlots * kSlotBytes;       // bf16 D boxes, 2 x 2 KB (unused for in-place fp32)
+  static constexpr int kOut2Off = kOutOff + (kAuxF32 ? 0 : 4096);
+};
+
+// 16-byte chunk j of row r inside a [32 x 64 B] SWIZZLE_64B box / a [32 x 128 B] SWIZZLE_128B box
+__device__ __forceinline__ uint32_t sw64(uint32_t base, int r, int j) { return base + r * 64 + ((j ^ ((r >> 1) & 3)) << 4); }
+__device__ __forceinline__ uint32_t sw128(uint32_t base, int r, int j) { return base + r * 128 + ((j ^ (r & 7)) << 4); }
+__device__ __forceinline__ void sts_u4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ uint4 lds_u4(uint32_t addr) {
+  uint4 r;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr));
+  return r;
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ float bf16_lo(uint32_t v) { return __uint_as_float(v << 16); }
+__device__ __forceinline__ float bf16_hi(uint32_t v) { return __uint_as_float(v & 0xFFFF0000u); }
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(map), "r"(src), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+template <int KIND, int CG, int BN, typename TD>
+__device__ __forceinline__ void epilogue_loop_tma(const EpiParams& ep, const EpiMaps& em, int M, int N, int tiles_n,
+                                                  uint32_t rank, Sched sched, uint32_t tmem_base, uint32_t wbuf,
+                                                  uint64_t* auxbar, uint64_t* tfull, uint64_t* tempty, int q, int half,
+                                                  int lane) {
+  using E = TmaEpi<KIND>;
+  constexpr int BMT = BM * CG, NCH = BN / kStageCols;
+  static_assert(sizeof(TD) == 2, "TMA epilogue: bf16 D");
+  // this warp's chunks of a tile that lie inside the matrix: chunk indices half, half + 2, ... (warp-uniform)
+  auto my_chunks = [&](const Seg& sgm) {
+    const int width = N - (sgm.tile % tiles_n) * BN;
+    const int nvalid = width >= BN ? NCH : (width + kStageCols - 1) / kStageCols;
+    return nvalid > half ? (nvalid - half + 1) / 2 : 0;
+  };
+  auto row0_of = [&](const Seg& sgm) { return (sgm.tile / tiles_n) * BMT + (int)rank * BM + q * 32; };
+  auto col0_of = [&](const Seg& sgm, int k) { return (sgm.tile % tiles_n) * BN + (half + 2 * k) * kStageCols; };
+
+  int acc = 0;
+  uint32_t acc_phase = 0;
+  // bias of a chunk: lane l holds bias[col0 + l], fetched one chunk ahead (also across tiles), broadcast by shuffles
+  auto load_bias = [&](const Seg& ts, int k) {
+    const int c = col0_of(ts, k) + lane;
+    return (ep.bias != nullptr && c < N) ? __ldg(ep.bias + c) : 0.f;
+  };
+  float b_next = 0.f;
+  int gbase = 0;        // chunks this warp completed in earlier tiles (ring position of the tile's first chunk)
+  int issued = 0;       // operand requests made, counted from the current tile's first chunk (may run into the next tile)
+  Seg sg, nx;
+  bool have = sched.next(sg);
+  if (have && my_chunks(sg) > 0) b_next = load_bias(sg, 0);
+  while (have) {
+    const bool have_next = sched.next(nx);
+    const int cnt = my_chunks(sg), cntn = have_next ? my_chunks(nx) : 0;
+    const int row0 = row0_of(sg);
+    if constexpr (E::kSlots > 0) {   // the next tile's operand rows -> L2, so the TMA requests above hit there
+      if (have_next)
+        epilogue_l2_prefetch<BN>((const char*)ep.aux, ep.ld_aux * (E::kAuxF32 ? 4 : 2), E::kAuxF32 ? 4 : 2, M, N,
+                                 (nx.tile / tiles_n) * BMT + (int)rank * BM, (nx.tile % tiles_n) * BN, q, half, lane);
+    }
+    const uint32_t taddr = tmem_base + acc * BN + ((uint32_t)(q * 32) << 16);
+    // request operand boxes up to kLook chunks ahead of chunk p (lane 0 issues; mbarrier per ring slot)
+    auto top_up = [&](int p) {
+      if constexpr (E::kSlots > 0) {
+        while (issued < p + E::kLook + 1 && issued < cnt + cntn) {
+          const bool in_next = issued >= cnt;
+          const Seg& ts = in_next ? nx : sg;
+          const int k = in_next ? issued - cnt : issued;
+          const int slot = (gbase + issued) % E::kSlots;
+          if (lane == 0) {
+            // in place (fp32): the slot still feeds the store of the chunk that used it last
+            if constexpr (E::kAuxF32) bulk_wait_read<0>();
+            const uint32_t bar = smem_u32(&auxbar[slot]);
+            mbar_expect_tx_u32(bar, 32 * kStageCols * (E::kAuxF32 ? 4 : 2));
+            tma_load_2d_u32(&em.aux, bar, wbuf + slot * E::kSlotBytes, col0_of(ts, k), row0_of(ts));
+          }
+          ++issued;
+        }
+      }
+    };
+    top_up(0);
+    mbar_wait(&tfull[acc], acc_phase);
+    tc_fence_after();
+#pragma unroll 1
+    for (int p = 0; p < cnt; ++p) {
+      const int G = gbase + p;                      // ring position
+      const int col0 = col0_of(sg, p);
+      const float b_cur = b_next;
+      if (p + 1 < cnt) b_next = load_bias(sg, p + 1);
+      else if (cntn > 0) b_next = load_bias(nx, 0);
+      float v[32];
+      tmem_ld32(taddr + (half + 2 * p) * kStageCols, v);
+      if (ep.bias != nullptr) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] += __shfl_sync(0xffffffffu, b_cur, i);
+      }
+      top_up(p);                    // keeps kLook operand boxes in flight (into the next tile at the end of this one)
+      const int ob = G & 1;
+      // the D / out2 boxes of this parity were handed to the store issued two chunks ago
+      if (lane == 0) bulk_wait_read<1>();
+      __syncwarp();
+      const uint32_t outb = wbuf + E::kOutOff + ob * 2048, out2b = wbuf + E::kOut2Off + ob * 2048;
+      if constexpr (KIND == kEpiNone) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          sts_u4(sw64(outb, lane, j), pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
+                 pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
+      } else if constexpr (KIND == kEpiGelu || KIND == kEpiSilu) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          uint32_t h[4], a[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            h[i] = pack_bf16x2(v[8 * j + 2 * i], v[8 * j + 2 * i + 1]);     // the pre-activation backward will see
+            const float x0 = bf16_lo(h[i]), x1 = bf16_hi(h[i]);
+            a[i] = KIND == kEpiGelu ? pack_bf16x2(gelu_fast(x0), gelu_fast(x1)) : pack_bf16x2(silu_fast(x0), silu_fast(x1));
+          }
+          if (ep.out2) sts_u4(sw64(out2b, lane, j), h[0], h[1], h[2], h[3]);
+          sts_u4(sw64(outb, lane, j), a[0], a[1], a[2], a[3]);
+        }
+      } else if constexpr (E::kAuxBf16) {
+        const int slot = G % E::kSlots;
+        mbar_wait(&auxbar[slot], (uint32_t)(G / E::kSlots) & 1u);
+        const uint32_t ab = wbuf + slot * E::kSlotBytes;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint4 hv = lds_u4(sw64(ab, lane, j));
+          const uint32_t hw[4] = {hv.x, hv.y, hv.z, hv.w};
+          uint32_t o[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float h0 = bf16_lo(hw[i]), h1 = bf16_hi(hw[i]);
+            const float d0 = KIND == kEpiDGelu ? gelu_grad_fast(h0) : silu_grad_fast(h0);
+            const float d1 = KIND == kEpiDGelu ? gelu_grad_fast(h1) : silu_grad_fast(h1);
+            o[i] = pack_bf16x2(v[8 * j + 2 * i] * d0, v[8 * j + 2 * i + 1] * d1);
+          }
+          sts_u4(sw64(outb, lane, j), o[0], o[1], o[2], o[3]);
+        }
+      }
+      fence_proxy_async();          // this thread's box writes -> visible to the TMA engine
+      __syncwarp();
+      if (lane == 0) {
+        tma_store_2d(&em.d, outb, col0, row0);
+        if constexpr (E::kOut2) {
+          if (ep.out2) tma_store_2d(&em.o2, out2b, col0, row0);
+        }
+        bulk_commit();
+      }
+    }
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) {
+      if constexpr (CG == 1) mbar_arrive(&tempty[acc]);
+      else mbar_arrive_cluster(mapa_u32(smem_u32(&tempty[acc]), 0));
+    }
+    if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    gbase += cnt;
+    issued -= cnt;
+    sg = nx;
+    have = have_next;
+  }
+  if (lane == 0) bulk_wait_all();   // the boxes must outlive their stores
+  __syncwarp();
+}
+
 template <int CG, int BN, int A_MN, int B_MN, typename TD>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                    TD* __restrict__ D, int64_t ldd, int M, int N, int K, EpiParams ep, int stream_k, int dbg) {
+                    const __grid_constant__ EpiMaps emaps, TD* __restrict__ D, int64_t ldd, int M, int N, int K,
+                    EpiParams ep, int stream_k, int dbg, int stages, int epi_bytes, int tma_epi) {
+  // stages / epi_bytes: pipeline depth and size of the epilogue's shared-memory region (host: GemmCfg::stages_for);
+  // tma_epi: 1 = TMA epilogue (epilogue_loop_tma; emaps valid), 0 = register / LSU epilogue
   // stream_k: 0 = data-parallel; n >= 1 = split mode with n k-slices for the tiles of the last partial round
   // dbg (profiling only, results are garbage): 1 = no TMA (MMA does not wait for operands), 2 = no MMA issue,
   // 4 = no epilogue work (accumulators released immediately); 8 = column-major tile order (results stay correct)
   using Cfg = GemmCfg<CG, BN>;
-  constexpr int S = Cfg::kStages;
+  const int S = stages;
   constexpr int BNL = Cfg::kBNL;
   constexpr int BMT = BM * CG;                 // output-tile rows of the CTA (pair)
   extern __shared__ uint8_t smem_raw[];
@@ -288,13 +494,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   // the shared address space (ld.shared / st.shared for the epilogue staging, not generic accesses)
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* stage_base = smem;
-  float* staging = reinterpret_cast<float*>(smem + S * Cfg::kStageBytes);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S * Cfg::kStageBytes + Cfg::kStagingBytes);
-  uint64_t* full = bars;              // [S]   TMA bytes landed (CG = 2: the leader's copy counts both CTAs' bytes)
-  uint64_t* empty = bars + S;         // [S]   MMAs reading the stage retired (arrives in every CTA of the pair)
-  uint64_t* tfull = bars + 2 * S;     // [2]   accumulator complete (arrives in every CTA of the pair)
-  uint64_t* tempty = bars + 2 * S + 2;  // [2] accumulator drained by all epilogue warps (of both CTAs; leader's copy)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S + 4);
+  uint8_t* epi_region = smem + S * Cfg::kStageBytes;      // 1024-byte aligned (kStageBytes is a multiple of 1024)
+  float* staging = reinterpret_cast<float*>(epi_region);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(epi_region + epi_bytes);
+  uint64_t* full = bars;              // [<=8] TMA bytes landed (CG = 2: the leader's copy counts both CTAs' bytes)
+  uint64_t* empty = bars + 8;         // [<=8] MMAs reading the stage retired (arrives in every CTA of the pair)
+  uint64_t* tfull = bars + 16;        // [2]   accumulator complete (arrives in every CTA of the pair)
+  uint64_t* tempty = bars + 18;       // [2]   accumulator drained by all epilogue warps (of both CTAs; leader's copy)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
+  uint64_t* auxbars = bars + 24;      // [8 warps][4] operand boxes of the TMA epilogue landed
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = CG == 1 ? 0u : cluster_ctarank();
@@ -308,6 +516,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_a);
     tma_prefetch_desc(&map_b);
+    if (tma_epi) {
+      tma_prefetch_desc(&emaps.d);
+      if (ep.out2 != nullptr) tma_prefetch_desc(&emaps.o2);
+      if (ep.aux != nullptr) tma_prefetch_desc(&emaps.aux);
+    }
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < S; ++s) {
@@ -318,6 +531,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       mbar_init(&tfull[s], 1);
       mbar_init(&tempty[s], kEpiWarps * CG);
     }
+    for (int s = 0; s < kEpiWarps * 4; ++s) mbar_init(&auxbars[s], 1);
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc<CG>(tmem_slot, Cfg::kTmemCols);
@@ -443,6 +657,19 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     int acc = 0;
     uint32_t acc_phase = 0;
     Sched sched(stream_k, tiles_m, tiles_n, ragged, num_kb, worker, workers, (dbg >> 3) & 1);
+    if (tma_epi && !(dbg & 4)) {
+      const uint32_t wbuf = smem_u32(epi_region) + (warp - kFirstEpiWarp) * (epi_bytes / kEpiWarps);
+      uint64_t* ab = auxbars + (warp - kFirstEpiWarp) * 4;
+#define REED_TMA_EPI(KIND) epilogue_loop_tma<KIND, CG, BN, TD>(ep, emaps, M, N, tiles_n, rank, sched, tmem_base, wbuf, ab, tfull, tempty, q, half, lane)
+      if constexpr (sizeof(TD) == 2) {
+        if (ep.kind == kEpiNone) REED_TMA_EPI(kEpiNone);
+        else if (ep.kind == kEpiGelu) REED_TMA_EPI(kEpiGelu);
+        else if (ep.kind == kEpiSilu) REED_TMA_EPI(kEpiSilu);
+        else if (ep.kind == kEpiDGelu) REED_TMA_EPI(kEpiDGelu);
+        else REED_TMA_EPI(kEpiDSilu);
+      }
+#undef REED_TMA_EPI
+    } else {
     // global operand of the fused epilogue, if any (see epilogue_l2_prefetch)
     const char* aux = nullptr;
     int64_t aux_pitch = 0;
@@ -490,6 +717,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       sg = nx;
       have = have_next;
     }
+    }
   }
   tc_fence_before();
   __syncwarp();
@@ -503,21 +731,31 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
 // ------------------------------------------------------------------------------------------------
 template <int CG, int BN, int A_MN, int B_MN, typename TD>
 static int launch(const CUtensorMap& ma, const CUtensorMap& mb, void* D, int64_t ldd, int M, int N, int K,
-                  const EpiParams& ep, cudaStream_t st, int grid, int stream_k) {
+                  const EpiParams& ep, cudaStream_t st, int grid, int stream_k, const EpiMaps* em) {
   static const int dbg = getenv("REED_GEMM_DEBUG") ? atoi(getenv("REED_GEMM_DEBUG")) : 0;
   using Cfg = GemmCfg<CG, BN>;
-  static_assert(Cfg::kStages >= 3, "pipeline too shallow");
+  static_assert(Cfg::stages_for(Cfg::kStagingBytes) >= 3, "pipeline too shallow");
   static_assert(!B_MN || Cfg::kBNL % 64 == 0, "MN-major B is staged in 64-column TMA boxes");
+  constexpr bool kTmaFits = Cfg::stages_for(Cfg::kTmaEpiAuxBytes) >= 3 && sizeof(TD) == 2;
+  const int tma_epi = (em != nullptr && kTmaFits) ? 1 : 0;
+  const bool fused_operand = ep.kind == kEpiDGelu || ep.kind == kEpiDSilu;
+  const int epi_bytes = tma_epi ? (fused_operand ? Cfg::kTmaEpiAuxBytes : Cfg::kTmaEpiBytes) : Cfg::kStagingBytes;
+  const int stages = Cfg::stages_for(epi_bytes);
+  const int smem = Cfg::smem_bytes(stages, epi_bytes);
   auto kernel = gemm_tcgen05_kernel<CG, BN, A_MN, B_MN, TD>;
   static bool configured = false;   // per template instance
   if (!configured) {
-    REED_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    const int a = Cfg::smem_bytes(Cfg::stages_for(Cfg::kStagingBytes), Cfg::kStagingBytes);
+    const int b0 = kTmaFits ? Cfg::smem_bytes(Cfg::stages_for(Cfg::kTmaEpiBytes), Cfg::kTmaEpiBytes) : 0;
+    const int b1 = kTmaFits ? Cfg::smem_bytes(Cfg::stages_for(Cfg::kTmaEpiAuxBytes), Cfg::kTmaEpiAuxBytes) : 0;
+    const int b = b0 > b1 ? b0 : b1;
+    REED_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, a > b ? a : b));
     configured = true;
   }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(kGemmThreads);
-  cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+  cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
   static const int pdl = getenv("REED_PDL") ? atoi(getenv("REED_PDL")) : 1;
   cudaLaunchAttribute attr[2];
@@ -529,28 +767,31 @@ static int launch(const CUtensorMap& ma, const CUtensorMap& mb, void* D, int64_t
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl ? 2 : 1;
-  REED_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kernel, ma, mb, (TD*)D, ldd, M, N, K, ep, stream_k, dbg));
+  static const EpiMaps no_maps{};
+  REED_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kernel, ma, mb, tma_epi ? *em : no_maps, (TD*)D, ldd, M, N, K, ep, stream_k, dbg,
+                                     stages, epi_bytes, tma_epi));
   return 0;
 }
 
 template <int CG, int BN, typename TD>
 static int launch_major(int a_mn, int b_mn, const CUtensorMap& ma, const CUtensorMap& mb, void* D, int64_t ldd, int M,
-                        int N, int K, const EpiParams& ep, cudaStream_t st, int grid, int stream_k) {
-  if (!a_mn && !b_mn) return launch<CG, BN, 0, 0, TD>(ma, mb, D, ldd, M, N, K, ep, st, grid, stream_k);
+                        int N, int K, const EpiParams& ep, cudaStream_t st, int grid, int stream_k, const EpiMaps* em) {
+  if (!a_mn && !b_mn) return launch<CG, BN, 0, 0, TD>(ma, mb, D, ldd, M, N, K, ep, st, grid, stream_k, em);
   if constexpr ((BN / CG) % 64 == 0) {
-    if (!a_mn && b_mn) return launch<CG, BN, 0, 1, TD>(ma, mb, D, ldd, M, N, K, ep, st, grid, stream_k);
-    if (a_mn && b_mn) return launch<CG, BN, 1, 1, TD>(ma, mb, D, ldd, M, N, K, ep, st, grid, stream_k);
+    if (!a_mn && b_mn) return launch<CG, BN, 0, 1, TD>(ma, mb, D, ldd, M, N, K, ep, st, grid, stream_k, em);
+    if (a_mn && b_mn) return launch<CG, BN, 1, 1, TD>(ma, mb, D, ldd, M, N, K, ep, st, grid, stream_k, em);
   }
-  if (a_mn && !b_mn) return launch<CG, BN, 1, 0, TD>(ma, mb, D, ldd, M, N, K, ep, st, grid, stream_k);
+  if (a_mn && !b_mn) return launch<CG, BN, 1, 0, TD>(ma, mb, D, ldd, M, N, K, ep, st, grid, stream_k, em);
   return fail("gemm_tcgen05: no kernel for cta_group::%d BN=%d with MN-major B", CG, BN);
 }
 
 template <int CG>
 static int launch_cg(int bn, int a_mn, int b_mn, const CUtensorMap& ma, const CUtensorMap& mb, void* D, int64_t ldd,
-                     int d_dtype, int M, int N, int K, const EpiParams& ep, cudaStream_t st, int grid, int stream_k) {
+                     int d_dtype, int M, int N, int K, const EpiParams& ep, cudaStream_t st, int grid, int stream_k,
+                     const EpiMaps* em) {
 #define GO(BNV)                                                                                                        \
-  (d_dtype == kF32 ? launch_major<CG, BNV, float>(a_mn, b_mn, ma, mb, D, ldd, M, N, K, ep, st, grid, stream_k)         \
-                   : launch_major<CG, BNV, bf16>(a_mn, b_mn, ma, mb, D, ldd, M, N, K, ep, st, grid, stream_k))
+  (d_dtype == kF32 ? launch_major<CG, BNV, float>(a_mn, b_mn, ma, mb, D, ldd, M, N, K, ep, st, grid, stream_k, em)     \
+                   : launch_major<CG, BNV, bf16>(a_mn, b_mn, ma, mb, D, ldd, M, N, K, ep, st, grid, stream_k, em))
   if (bn == 256) return GO(256);
   if (bn == 192) return GO(192);
   return GO(128);
