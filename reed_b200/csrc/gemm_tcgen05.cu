@@ -48,17 +48,19 @@ static int make_map(CUtensorMap* map, const void* ptr, int64_t rows, int64_t col
 
 // [32 rows x 32 columns] box over a row-major [rows, cols] matrix for the TMA epilogue: bf16 -> 64-byte rows with
 // SWIZZLE_64B, fp32 -> 128-byte rows with SWIZZLE_128B (one epilogue warp's share of a 32-column chunk)
-static int make_epi_map(CUtensorMap* map, const void* ptr, int dtype, int64_t rows, int64_t cols, int64_t ld) {
+static int make_epi_map(CUtensorMap* map, const void* ptr, int dtype, int64_t rows, int64_t cols, int64_t ld, int box_cols = 32) {
   EncodeTiledFn enc = get_encode_fn();
   REED_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled is not available from the driver");
   const int esz = dtype == kF32 ? 4 : 2;
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
   cuuint64_t strides[1] = {(cuuint64_t)ld * esz};
-  cuuint32_t box[2] = {32u, 32u};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, 32u};
   cuuint32_t estr[2] = {1u, 1u};
+  const int row_bytes = box_cols * esz;   // 128 / 64 / 32-byte box rows take the swizzle of the same span
+  const CUtensorMapSwizzle swz = row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
   CUresult r = enc(map, dtype == kF32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
                    const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   dtype == kF32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   REED_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled (epilogue box) failed (%d) rows=%lld cols=%lld ld=%lld", (int)r,
                (long long)rows, (long long)cols, (long long)ld);
@@ -193,16 +195,20 @@ int gemm_tcgen05(const void* A, int64_t lda, int a_mn, const void* B, int64_t ld
   const bool want_o2 = ep.out2 != nullptr && (ep.kind == kEpiGelu || ep.kind == kEpiSilu || ep.kind == kEpiGateRes);
   const bool has_aux = ep.kind == kEpiDGelu || ep.kind == kEpiDSilu || ep.kind == kEpiGateRes;
   // REED_TMA_EPI: bit 0 = activation-gradient kinds (fused operand), bit 1 = activation kinds, bit 2 = plain bf16 stores
-  const int kind_bit = (ep.kind == kEpiDGelu || ep.kind == kEpiDSilu) ? 1 : ((ep.kind == kEpiGelu || ep.kind == kEpiSilu) ? 2 : 4);
-  bool tma = (tma_epi_on & kind_bit) && !p.stream_k && !ep.accumulate && d_dtype == kBF16 && act_kind &&
+  // bit 3 = gate+residual (fp32 D, 16-column chunks; off by default: measured equal to the register path, whose
+  // exposed cost on these two-round GEMMs is the HBM traffic of the last round, not operand latency)
+  const int kind_bit = ep.kind == kEpiGateRes ? 8 : ((ep.kind == kEpiDGelu || ep.kind == kEpiDSilu) ? 1 : ((ep.kind == kEpiGelu || ep.kind == kEpiSilu) ? 2 : 4));
+  const bool gate_res = ep.kind == kEpiGateRes && d_dtype == kF32 && ep.rows_per_group % 32 == 0 && N % 16 == 0;
+  bool tma = (tma_epi_on & kind_bit) && !p.stream_k && !ep.accumulate && ((d_dtype == kBF16 && act_kind) || gate_res) &&
              tma_ok_ptr(D, ldd, d_dtype == kF32 ? 4 : 2) && (!want_o2 || tma_ok_ptr(ep.out2, ep.ld_out2, 2)) &&
              (!has_aux || tma_ok_ptr(ep.aux, ep.ld_aux, ep.kind == kEpiGateRes ? 4 : 2)) &&
              (ep.bias == nullptr || ((uintptr_t)ep.bias & 15) == 0) &&
              (ep.kind != kEpiGateRes || (((uintptr_t)ep.gate & 15) == 0 && ep.ld_gate % 4 == 0));
   if (tma) {
-    if (make_epi_map(&em.d, D, d_dtype, M, N, ldd)) return 1;
-    if (want_o2) { if (make_epi_map(&em.o2, ep.out2, kBF16, M, N, ep.ld_out2)) return 1; } else em.o2 = em.d;
-    if (has_aux) { if (make_epi_map(&em.aux, ep.aux, ep.kind == kEpiGateRes ? kF32 : kBF16, M, N, ep.ld_aux)) return 1; } else em.aux = em.d;
+    const int bw = gate_res ? 16 : 32;     // chunk width of the epilogue variant
+    if (make_epi_map(&em.d, D, d_dtype, M, N, ldd, bw)) return 1;
+    if (want_o2) { if (make_epi_map(&em.o2, ep.out2, kBF16, M, N, ep.ld_out2, bw)) return 1; } else em.o2 = em.d;
+    if (has_aux) { if (make_epi_map(&em.aux, ep.aux, ep.kind == kEpiGateRes ? kF32 : kBF16, M, N, ep.ld_aux, bw)) return 1; } else em.aux = em.d;
     emp = &em;
   }
   if (p.cg == 2) return gemm_tc_launch_cg2(p.bn, a_mn, b_mn, ma, mb, D, ldd, d_dtype, M, N, K, ep, st, p.grid, p.stream_k, emp);

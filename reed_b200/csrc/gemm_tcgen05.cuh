@@ -475,6 +475,138 @@ __device__ __forceinline__ void epilogue_loop_tma(const EpiParams& ep, const Epi
   __syncwarp();
 }
 
+// TMA epilogue of the adaLN-Zero gate + residual GEMMs (attn.proj / mlp.fc2, sit.py:134-135): fp32 D = res + gate * bf16(y),
+// y = acc + bias -> out2 (bf16).  Chunks are 16 columns wide so that three fp32 residual boxes ([32 x 16], 2 KB,
+// SWIZZLE_64B) and two bf16 y boxes ([32 x 16], 1 KB, SWIZZLE_32B) fit the 8 KB per-warp region that keeps the
+// pipeline at full depth.  The residual box is requested two chunks ahead, updated IN PLACE (thread = row) and
+// stored back by TMA; a slot is re-requested only after the store that last used it has read it.
+// Bias and gate ride in one register per chunk: lanes 0-15 hold bias[col0 + l], lanes 16-31 gate[g, col0 + l - 16].
+__device__ __forceinline__ uint32_t sw32(uint32_t base, int r, int j) { return base + r * 32 + ((j ^ ((r >> 2) & 1)) << 4); }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+template <int CG, int BN>
+__device__ __forceinline__ void epilogue_loop_tma_gateres(const EpiParams& ep, const EpiMaps& em, int M, int N, int tiles_n,
+                                                          uint32_t rank, Sched sched, uint32_t tmem_base, uint32_t wbuf,
+                                                          uint64_t* auxbar, uint64_t* tfull, uint64_t* tempty, int q,
+                                                          int half, int lane) {
+  constexpr int BMT = BM * CG, W = 16, NCH = BN / W, kSlots = 3, kLook = 2, kSlotBytes = 2048;
+  constexpr int kOut2Off = kSlots * kSlotBytes;
+  auto my_chunks = [&](const Seg& sgm) {
+    const int width = N - (sgm.tile % tiles_n) * BN;
+    const int nvalid = width >= BN ? NCH : (width + W - 1) / W;
+    return nvalid > half ? (nvalid - half + 1) / 2 : 0;
+  };
+  auto row0_of = [&](const Seg& sgm) { return (sgm.tile / tiles_n) * BMT + (int)rank * BM + q * 32; };
+  auto col0_of = [&](const Seg& sgm, int k) { return (sgm.tile % tiles_n) * BN + (half + 2 * k) * W; };
+  auto load_bg = [&](const Seg& ts, int k) {
+    const int c = col0_of(ts, k) + (lane & 15);
+    if (c >= N) return 0.f;
+    if (lane < 16) return ep.bias != nullptr ? __ldg(ep.bias + c) : 0.f;
+    const int r0 = row0_of(ts);
+    return __ldg(ep.gate + (int64_t)((r0 < M ? r0 : M - 1) / ep.rows_per_group) * ep.ld_gate + c);
+  };
+  int acc = 0;
+  uint32_t acc_phase = 0;
+  float bg_next = 0.f;
+  int gbase = 0, issued = 0;
+  Seg sg, nx;
+  bool have = sched.next(sg);
+  if (have && my_chunks(sg) > 0) bg_next = load_bg(sg, 0);
+  while (have) {
+    const bool have_next = sched.next(nx);
+    const int cnt = my_chunks(sg), cntn = have_next ? my_chunks(nx) : 0;
+    const int row0 = row0_of(sg);
+    if (have_next)
+      epilogue_l2_prefetch<BN>((const char*)ep.aux, ep.ld_aux * 4, 4, M, N, (nx.tile / tiles_n) * BMT + (int)rank * BM,
+                               (nx.tile % tiles_n) * BN, q, half, lane);
+    const uint32_t taddr = tmem_base + acc * BN + ((uint32_t)(q * 32) << 16);
+    auto top_up = [&](int p) {
+      while (issued < p + kLook + 1 && issued < cnt + cntn) {
+        const bool in_next = issued >= cnt;
+        const Seg& ts = in_next ? nx : sg;
+        const int k = in_next ? issued - cnt : issued;
+        const int slot = (gbase + issued) % kSlots;
+        if (lane == 0) {
+          bulk_wait_read<0>();      // in place: the slot fed the store of the chunk that used it last
+          const uint32_t bar = smem_u32(&auxbar[slot]);
+          mbar_expect_tx_u32(bar, 32 * W * 4);
+          tma_load_2d_u32(&em.aux, bar, wbuf + slot * kSlotBytes, col0_of(ts, k), row0_of(ts));
+        }
+        ++issued;
+      }
+    };
+    top_up(0);
+    mbar_wait(&tfull[acc], acc_phase);
+    tc_fence_after();
+#pragma unroll 1
+    for (int p = 0; p < cnt; ++p) {
+      const int G = gbase + p;
+      const int col0 = col0_of(sg, p);
+      const float bg = bg_next;
+      if (p + 1 < cnt) bg_next = load_bg(sg, p + 1);
+      else if (cntn > 0) bg_next = load_bg(nx, 0);
+      float v[16];
+      tmem_ld16(taddr + (half + 2 * p) * W, v);
+      top_up(p);
+      const int slot = G % kSlots;
+      const uint32_t ab = wbuf + slot * kSlotBytes, out2b = wbuf + kOut2Off + (G & 1) * 1024;
+      uint32_t y[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        y[i] = pack_bf16x2(v[2 * i] + __shfl_sync(0xffffffffu, bg, 2 * i), v[2 * i + 1] + __shfl_sync(0xffffffffu, bg, 2 * i + 1));
+      if (lane == 0) bulk_wait_read<1>();     // the y box of this parity went out two chunks ago
+      __syncwarp();
+      if (ep.out2) {
+        sts_u4(sw32(out2b, lane, 0), y[0], y[1], y[2], y[3]);
+        sts_u4(sw32(out2b, lane, 1), y[4], y[5], y[6], y[7]);
+      }
+      mbar_wait(&auxbar[slot], (uint32_t)(G / kSlots) & 1u);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint32_t ra = sw64(ab, lane, j);
+        const uint4 rv = lds_u4(ra);
+        const float g0 = __shfl_sync(0xffffffffu, bg, 16 + 4 * j), g1 = __shfl_sync(0xffffffffu, bg, 17 + 4 * j);
+        const float g2 = __shfl_sync(0xffffffffu, bg, 18 + 4 * j), g3 = __shfl_sync(0xffffffffu, bg, 19 + 4 * j);
+        const float o0 = __uint_as_float(rv.x) + g0 * bf16_lo(y[2 * j]);
+        const float o1 = __uint_as_float(rv.y) + g1 * bf16_hi(y[2 * j]);
+        const float o2 = __uint_as_float(rv.z) + g2 * bf16_lo(y[2 * j + 1]);
+        const float o3 = __uint_as_float(rv.w) + g3 * bf16_hi(y[2 * j + 1]);
+        sts_u4(ra, __float_as_uint(o0), __float_as_uint(o1), __float_as_uint(o2), __float_as_uint(o3));
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) {
+        tma_store_2d(&em.d, ab, col0, row0);
+        if (ep.out2) tma_store_2d(&em.o2, out2b, col0, row0);
+        bulk_commit();
+      }
+    }
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) {
+      if constexpr (CG == 1) mbar_arrive(&tempty[acc]);
+      else mbar_arrive_cluster(mapa_u32(smem_u32(&tempty[acc]), 0));
+    }
+    if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    gbase += cnt;
+    issued -= cnt;
+    sg = nx;
+    have = have_next;
+  }
+  if (lane == 0) bulk_wait_all();
+  __syncwarp();
+}
+
 template <int CG, int BN, int A_MN, int B_MN, typename TD>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
@@ -661,7 +793,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       const uint32_t wbuf = smem_u32(epi_region) + (warp - kFirstEpiWarp) * (epi_bytes / kEpiWarps);
       uint64_t* ab = auxbars + (warp - kFirstEpiWarp) * 4;
 #define REED_TMA_EPI(KIND) epilogue_loop_tma<KIND, CG, BN, TD>(ep, emaps, M, N, tiles_n, rank, sched, tmem_base, wbuf, ab, tfull, tempty, q, half, lane)
-      if constexpr (sizeof(TD) == 2) {
+      if constexpr (sizeof(TD) == 4) {
+        epilogue_loop_tma_gateres<CG, BN>(ep, emaps, M, N, tiles_n, rank, sched, tmem_base, wbuf, ab, tfull, tempty, q, half, lane);
+      } else {
         if (ep.kind == kEpiNone) REED_TMA_EPI(kEpiNone);
         else if (ep.kind == kEpiGelu) REED_TMA_EPI(kEpiGelu);
         else if (ep.kind == kEpiSilu) REED_TMA_EPI(kEpiSilu);
@@ -736,7 +870,7 @@ static int launch(const CUtensorMap& ma, const CUtensorMap& mb, void* D, int64_t
   using Cfg = GemmCfg<CG, BN>;
   static_assert(Cfg::stages_for(Cfg::kStagingBytes) >= 3, "pipeline too shallow");
   static_assert(!B_MN || Cfg::kBNL % 64 == 0, "MN-major B is staged in 64-column TMA boxes");
-  constexpr bool kTmaFits = Cfg::stages_for(Cfg::kTmaEpiAuxBytes) >= 3 && sizeof(TD) == 2;
+  constexpr bool kTmaFits = Cfg::stages_for(Cfg::kTmaEpiAuxBytes) >= 3;
   const int tma_epi = (em != nullptr && kTmaFits) ? 1 : 0;
   const bool fused_operand = ep.kind == kEpiDGelu || ep.kind == kEpiDSilu;
   const int epi_bytes = tma_epi ? (fused_operand ? Cfg::kTmaEpiAuxBytes : Cfg::kTmaEpiBytes) : Cfg::kStagingBytes;
