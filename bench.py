@@ -339,9 +339,16 @@ def run_gpu_arm(args, cfg):
         except Exception:
             pass
         peak = peaks.get("bf16_tflops_sustained") or 1400.0
+        traffic = None     # DRAM bytes per GEMM launch, from the committed ncu capture of the same step (xl2 workload only)
+        try:
+            if args.config == "xl2":
+                traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_gemm_traffic.json")))["dram_bytes_per_launch"]
+        except Exception:
+            pass
         achieved = flops / (tms * 1e-3) / 1e12 if tms > 0 else 0.0
         roof = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                "traffic": None, "kernel": "gemm_tcgen05_kernel", "launches_timed": len(records),
+                "traffic": traffic, "traffic_source": "profiles/r01_gemm_traffic.json (ncu dram bytes, mean per launch)"
+                if traffic is not None else None, "kernel": "gemm_tcgen05_kernel", "launches_timed": len(records),
                 "avg_launch_us": tms * 1e3 / len(records),
                 "method": "all tcgen05 GEMM launches of one train step replayed back to back in a CUDA graph, CUDA events",
                 "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)"
