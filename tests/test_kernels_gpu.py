@@ -119,6 +119,36 @@ def test_gemm_epilogues(ops, mode):
         assert _rel(got.float(), want) < tol
 
 
+@pytest.mark.parametrize("bn", [0, 1, 2, 3])                   # planner's choice / tile width 128 / 192 / 256
+def test_gemm_tma_epilogue_many_tiles(ops, bn):
+    """bf16 outputs leave through the TMA epilogue: every persistent CTA walks several tiles, so the per-warp operand
+    ring, the bias look-ahead and the store boxes carry over tile boundaries; M and N are ragged (N % 32 == 8)."""
+    ops.set_backends(gemm=ops.BACKEND_TENSOR_CG2 + 8 * bn)
+    M, N, K = 40000 + 24, 1000, 128
+    a, w, _, _ = _operands(M, N, K, 0, 0, torch.bfloat16)
+    bias = _rand(N, seed=3)
+    acc = a.float() @ w.float().t() + bias
+    out = ops.gemm(a, w, out_dtype=torch.bfloat16, bias=bias)
+    assert _rel(out.float(), acc) < 1e-2
+    h = torch.empty(M, N, device=DEV, dtype=torch.bfloat16)
+    y = ops.gemm(a, w, out_dtype=torch.bfloat16, bias=bias, epilogue=ops.EPI_GELU, out2=h)
+    assert _rel(h.float(), acc) < 1e-2
+    assert _rel(y.float(), F.gelu(h.float(), approximate="tanh")) < 1.5e-2
+    if bn == 2:
+        return                                             # MN-major B has no 192-wide pair tile (96 columns per CTA)
+    # dgrad through the activation: D[M, K] = (dy[M, N] W[N, K]) * gelu'(hsave[M, K]); W read MN-major
+    K2 = 768
+    w2 = _rand(N, K2, dtype=torch.bfloat16, scale=N ** -0.5, seed=8)
+    dy = _rand(M, N, dtype=torch.bfloat16, seed=6)
+    hsave = _rand(M, K2, dtype=torch.bfloat16, seed=7)
+    hv = hsave.float().requires_grad_(True)
+    (grad,) = torch.autograd.grad(F.gelu(hv, approximate="tanh").sum(), hv)
+    want = (dy.float() @ w2.float()) * grad
+    got = ops.gemm(dy, w2, b_mn=True, out_dtype=torch.bfloat16, epilogue=ops.EPI_DGELU, aux=hsave)
+    torch.cuda.synchronize()
+    assert _rel(got.float(), want) < 1.5e-2
+
+
 @pytest.mark.parametrize("cg", [1, 2])
 @pytest.mark.parametrize("bn", [1, 2, 3])                      # tile width 128 / 192 / 256
 @pytest.mark.parametrize("layout", [(0, 0), (0, 1), (1, 1)])
