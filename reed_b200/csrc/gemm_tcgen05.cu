@@ -1,4 +1,4 @@
-// Host side of the tcgen05 GEMM: tensor maps, tile/cluster/stream-K plan, dispatch to the cta_group::1 / ::2 kernels.
+// Host side of the tcgen05 GEMM: tensor maps, tile / cluster / split-K plan, dispatch to the cta_group::1 / ::2 kernels.
 #include <cuda.h>
 #include <stdlib.h>
 #include "common.cuh"
@@ -93,7 +93,7 @@ static int sm_count() {
   return use < 2 ? 2 : use;
 }
 
-// Plan: cta_group (1 / 2), tile width BN, data-parallel or stream-K.  Cost model per k-block and per CTA, in SM
+// Plan: cta_group (1 / 2), tile width BN, data-parallel or split (k slices for the last partial round).  Cost model per k-block and per CTA, in SM
 // cycles: the MMA needs 2*BN (UMMA 128*CG x BN x 16 retires in BN/2 cycles), the operand fetch needs
 // (16 KB of A + BN/CG * 128 B of B) / ~42 B/clk (the measured L2->SM share of one SM, B300_MICROARCH.md "LTS cap";
 // 12-13 TB/s chip-wide measured here) - the larger of the two paces the tile; DP pays whole waves.
@@ -170,7 +170,7 @@ void gemm_tcgen05_force_bn(int bn) { g_force_bn = bn; }
 
 int gemm_tcgen05(const void* A, int64_t lda, int a_mn, const void* B, int64_t ldb, int b_mn, void* D, int64_t ldd,
                  int d_dtype, int M, int N, int K, const EpiParams& ep, cudaStream_t st) {
-  // stream-K needs an output that tolerates fp32 atomics: no epilogue, no bias, fp32 D (the weight gradients)
+  // the split mode needs an output that tolerates fp32 atomics: no epilogue, no bias, fp32 D (the weight gradients)
   const bool sk_ok = ep.kind == kEpiNone && d_dtype == kF32 && ep.bias == nullptr && ep.out2 == nullptr;
   const GemmPlan p = plan_gemm(M, N, K, b_mn, sk_ok, g_force_cg, g_force_bn);
   if (p.stream_k > 1 && !ep.accumulate) {

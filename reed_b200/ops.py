@@ -297,7 +297,7 @@ def linear(x, weight, bias, *, act=ACT_NONE, act_dtype, out_dtype=None):
 
 
 class _GradAccumulator:
-    """fp32 side buffer the consumers of a shared tensor add their input gradients into (one stream-K GEMM each),
+    """fp32 side buffer the consumers of a shared tensor add their input gradients into (one split-K GEMM each),
     instead of handing autograd 28 separate bf16 gradients to sum."""
 
     def __init__(self):
@@ -508,7 +508,7 @@ class SiTBlockFn(torch.autograd.Function):
         dw_ada = _weight_grad(w_ada, dmod_a, c_act)
         dc = None
         if ctx.needs_input_grad[1]:
-            if ctx.c_acc is not None:     # [B, 6D] x [6D, D]: few rows, long reduction -> stream-K adds into the side buffer
+            if ctx.c_acc is not None:     # [B, 6D] x [6D, D]: few rows, long reduction -> split-K slices add into the side buffer
                 gemm(dmod_a, W(w_ada), b_mn=True, out=ctx.c_acc.get(c_act), accumulate=True)
             else:
                 dc = gemm(dmod_a, W(w_ada), b_mn=True, out_dtype=act_dtype)

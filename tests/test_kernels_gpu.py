@@ -174,7 +174,8 @@ def test_gemm_ragged_last_column_tile(ops, shape, layout, bn, cg):
 @pytest.mark.parametrize("cg", [0, 1, 2])
 @pytest.mark.parametrize("shape", [(1152, 1152, 8192), (3456, 1152, 4096), (1152, 4608, 2048), (384, 1536, 8192)])
 def test_gemm_stream_k_wgrad(ops, shape, cg):
-    """Weight-gradient shapes whose tile count does not fill the SMs take the stream-K path (fp32 red.add partials)."""
+    """Weight-gradient shapes whose tile count does not fill the SMs take the split path: whole rounds data-parallel,
+    the last partial round cut into k slices that are added with fp32 red.add into rows zeroed beforehand."""
     ops.set_backends(gemm={0: ops.BACKEND_TENSOR, 1: ops.BACKEND_TENSOR_CG1, 2: ops.BACKEND_TENSOR_CG2}[cg])
     M, N, K = shape                                        # dW[M=N_out, N=K_in] = dy^T x, reduction over K tokens
     dy = _rand(K, M, dtype=torch.bfloat16, seed=11)
