@@ -130,3 +130,13 @@ def test_siloss_host_side_contract():
         a = fn.time_weight(t, 0.7, sched, [0.25, 0.75])
         b = loss_oracle.schedule_weight(t, 0.7, sched, (0.25, 0.75))
         assert torch.allclose(a, b, atol=1e-7), sched
+
+
+def test_gemm_reserve_sms_is_host_state():
+    """reed_gemm_reserve_sms only edits the host-side GEMM planner (no GPU needed) and rejects nonsense."""
+    from reed_b200 import _cabi
+    _cabi.load()
+    _cabi.call("reed_gemm_reserve_sms", 16)
+    _cabi.call("reed_gemm_reserve_sms", 0)
+    with pytest.raises(_cabi.ReedLibraryError):
+        _cabi.call("reed_gemm_reserve_sms", 1000)
