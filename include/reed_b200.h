@@ -49,6 +49,14 @@ int reed_gemm(int act_dtype, const void* A, int64_t lda, int a_mn_major, const v
               int64_t ld_aux, const void* gate, int64_t ld_gate, int rows_per_group, void* out2, int64_t ld_out2,
               int accumulate, int backend, void* stream);
 
+/* Weight gradient of a Linear together with its bias gradient, one tensor-core GEMM (bf16 operands, fp32 outputs):
+ *   dW[n_out, k_in] (+)= dy^T x   and   db[n_out] += sum_tokens dy       (autograd of timm Attention.qkv / Mlp.fc1,
+ *   models/sit.py:114-124).  dy is [tokens, n_out] (pitch ld_dy); x_ext is [tokens, k_in + 8] (pitch ld_x) with ones in
+ *   column k_in (written by reed_ln_modulate_fwd), so db is one more output column of the GEMM instead of a separate
+ *   reduction pass over dy.  db must be zeroed by the caller once per step; `accumulate` adds into dW. */
+int reed_gemm_wgrad_bias(const void* dy, int64_t ld_dy, const void* x_ext, int64_t ld_x, void* dW, int64_t ldd, void* db,
+                         int n_out, int k_in, int tokens, int accumulate, void* stream);
+
 /* Multi-head attention, non-causal, scale head_dim^-0.5, over the packed qkv GEMM output.
  * Replaces timm Attention.forward's reshape/permute + F.scaled_dot_product_attention (models/sit.py:13,114-118,134).
  *   qkv [B,T,3,H,hd] (act dtype) -> o [B,T,H,hd] (act dtype), lse [B,H,T] fp32 (saved for backward). */
@@ -69,9 +77,12 @@ int reed_qk_norm_bwd(const void* dout, int act_dtype, const void* qkv, const voi
 
 /* out = LayerNorm(x; no affine, eps) * (1 + scale[g]) + shift[g], g = row / rows_per_group.
  * Replaces norm1/norm2/norm_final + modulate (models/sit.py:26-27,113,119,134-135,146,155).
- *   x fp32 [M,D]; shift/scale fp32 rows of pitch ld_mod; out act dtype [M,D]; mean/rstd fp32 [M] (saved). */
+ *   x fp32 [M,D]; shift/scale fp32 rows of pitch ld_mod; out act dtype, rows of pitch ld_out >= D (multiple of 8);
+ *   mean/rstd fp32 [M] (saved).  With bf16 output and ld_out >= D + 8 every row also gets [1,0,0,0,0,0,0,0] at columns
+ *   D..D+7: the "ones column" reed_gemm_wgrad_bias contracts against to produce the bias gradient. */
 int reed_ln_modulate_fwd(const void* x, const void* shift, const void* scale, int64_t ld_mod, int rows_per_group,
-                         void* out, int act_dtype, void* mean, void* rstd, int M, int D, float eps, void* stream);
+                         void* out, int64_t ld_out, int act_dtype, void* mean, void* rstd, int M, int D, float eps,
+                         void* stream);
 /* dx = dres + LN-backward(dout * (1+scale)); dshift[g] += sum dout; dscale[g] += sum dout * xhat (fp32 atomics).
  * dres may be NULL.  Replaces autograd of the above plus the residual-gradient add. */
 int reed_ln_modulate_bwd(const void* dout, int act_dtype, const void* x, const void* mean, const void* rstd,

@@ -23,7 +23,8 @@ _SIGNATURES = {
     "reed_attn_bwd": [I, P, P, P, P, P, P, I, I, I, I, I, P],
     "reed_qk_norm_fwd": [P, I, P, P, P, P, P, P, L, I, I, F, P],
     "reed_qk_norm_bwd": [P, I, P, P, P, P, P, P, P, P, P, L, I, I, P],
-    "reed_ln_modulate_fwd": [P, P, P, L, I, P, I, P, P, I, I, F, P],
+    "reed_ln_modulate_fwd": [P, P, P, L, I, P, L, I, P, P, I, I, F, P],
+    "reed_gemm_wgrad_bias": [P, L, P, L, P, L, P, I, I, I, I, P],
     "reed_ln_modulate_bwd": [P, I, P, P, P, P, L, I, P, P, P, P, I, I, P],
     "reed_ln_modulate_gate_bwd": [P, I, P, P, P, P, L, I, P, P, P, P, P, P, P, P, P, I, I, P],
     "reed_gate_bwd": [P, P, I, P, L, I, P, P, P, I, I, P],

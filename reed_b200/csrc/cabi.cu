@@ -80,6 +80,7 @@ extern "C" int reed_gemm(int act_dtype, const void* A, int64_t lda, int a_mn_maj
   ep.kind = epilogue; ep.bias = (const float*)bias; ep.aux = aux; ep.ld_aux = ld_aux; ep.gate = (const float*)gate;
   ep.ld_gate = ld_gate; ep.rows_per_group = rows_per_group > 0 ? rows_per_group : 1; ep.out2 = out2; ep.ld_out2 = ld_out2;
   ep.accumulate = accumulate;
+  ep.bias_grad = nullptr; ep.n_store = 0;
   cudaStream_t st = (cudaStream_t)stream;
   const int force_bn = backend >> 3;       // test knob: bits 3+ of `backend` pin the tile width (1/2/3 = 128/192/256)
   backend &= 7;
@@ -99,6 +100,32 @@ extern "C" int reed_gemm(int act_dtype, const void* A, int64_t lda, int a_mn_maj
 }
 
 // qkv: [B, T, 3, H, hd] (act dtype); o: [B, T, H, hd]; lse: [B, H, T] fp32
+extern "C" int reed_colsum(const void* src, int src_dtype, int64_t ld, void* out, int M, int N, void* stream);
+
+// dW[n_out, k_in] (+)= dy^T x and db[n_out] += sum_tokens dy, in ONE weight-gradient GEMM: x_ext is the activation
+// matrix [tokens, k_in + 8] whose column k_in holds ones (reed_ln_modulate_fwd writes it when ld_out >= D + 8), so the
+// bias gradient is one more output column of the tensor-core GEMM instead of a separate pass over dy.
+// bf16 operands; falls back to GEMM + column-sum kernel when the tcgen05 path does not take the shape.
+extern "C" int reed_gemm_wgrad_bias(const void* dy, int64_t ld_dy, const void* x_ext, int64_t ld_x, void* dW, int64_t ldd,
+                                    void* db, int n_out, int k_in, int tokens, int accumulate, void* stream) {
+  REED_REQUIRE(n_out > 0 && k_in > 0 && tokens > 0 && k_in % 8 == 0 && ld_x >= k_in + 8, "gemm_wgrad_bias: bad shape");
+  REED_REQUIRE(db != nullptr, "gemm_wgrad_bias: bias gradient buffer missing");
+  EpiParams ep;
+  ep.kind = kEpiNone; ep.bias = nullptr; ep.aux = nullptr; ep.ld_aux = 0; ep.gate = nullptr; ep.ld_gate = 0;
+  ep.rows_per_group = 1; ep.out2 = nullptr; ep.ld_out2 = 0; ep.accumulate = accumulate;
+  ep.bias_grad = (float*)db; ep.n_store = k_in;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int N = k_in + 8;
+  if (tokens > 64 && gemm_tcgen05_supported(ld_dy, ld_x, ldd, dy, x_ext, n_out, N, tokens)) {
+    gemm_tcgen05_force_cta_group(0);
+    gemm_tcgen05_force_bn(0);
+    return gemm_tcgen05(dy, ld_dy, 1, x_ext, ld_x, 1, dW, ldd, kF32, n_out, N, tokens, ep, st);
+  }
+  ep.bias_grad = nullptr; ep.n_store = 0;
+  if (gemm_simt(kBF16, dy, ld_dy, 1, x_ext, ld_x, 1, dW, ldd, kF32, n_out, k_in, tokens, ep, st)) return 1;
+  return reed_colsum(dy, kBF16, ld_dy, db, tokens, n_out, stream);
+}
+
 // backend: 0 auto (tcgen05 kernel when T/hd allow, else mma.sync, else SIMT), 1 force SIMT, 2 require a tensor-core
 // kernel, 3 require the mma.sync kernel, 4 require the tcgen05 kernel
 static int attn_pick(int act_dtype, int T, int hd, int backend, int* which) {

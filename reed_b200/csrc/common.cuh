@@ -115,6 +115,11 @@ struct EpiParams {
   void* out2;             // act dtype [M, ld_out2] or null
   int64_t ld_out2;
   int accumulate;         // kEpiNone with fp32 D only
+  // Weight gradient that carries its bias gradient (tcgen05 path, kEpiNone, fp32 D): the B operand has a column of
+  // ones at index n_store, so column n_store of the product is sum_k A[k, row] - it is added to bias_grad[row]
+  // (atomically; the caller zeroes it) and columns >= n_store are not stored to D.  null = ordinary GEMM.
+  float* bias_grad;
+  int n_store;
 };
 
 // Applies the epilogue to 4 consecutive columns of one row.  TD = type of D, TA = activation type.

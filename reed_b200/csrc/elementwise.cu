@@ -58,7 +58,7 @@ constexpr int kLnStages = 2;
 template <typename TA, int MAXV>
 __global__ void __launch_bounds__(kLnWarps * 32) ln_modulate_fwd_kernel(
     const float* __restrict__ x, const float* __restrict__ shift, const float* __restrict__ scale, int64_t ld_mod,
-    int rows_per_group, int rows_per_cta, TA* __restrict__ out, float* __restrict__ mean_out,
+    int rows_per_group, int rows_per_cta, TA* __restrict__ out, int64_t ld_out, float* __restrict__ mean_out,
     float* __restrict__ rstd_out, int M, int D, float eps) {
   pdl_launch();   // dependents (the next GEMM of the stream) may start their prologue
   extern __shared__ __align__(128) uint8_t ln_smem[];
@@ -139,7 +139,12 @@ __global__ void __launch_bounds__(kLnWarps * 32) ln_modulate_fwd_kernel(
       mean_out[row] = mean;
       rstd_out[row] = rstd;
     }
-    TA* o = out + (int64_t)row * D;
+    TA* o = out + (int64_t)row * ld_out;
+    if constexpr (sizeof(TA) == 2) {
+      // rows with 8 spare elements carry the "ones column" that lets a weight-gradient GEMM over this matrix produce
+      // the bias gradient as one more output column (reed_gemm_wgrad_bias): [1, 0, 0, 0, 0, 0, 0, 0] at column D
+      if (ld_out >= D + 8 && lane == 0) *reinterpret_cast<uint4*>(o + D) = make_uint4(0x00003F80u, 0u, 0u, 0u);
+    }
 #pragma unroll
     for (int i = 0; i < MAXV; ++i) {
       int col = (i * 32 + lane) * 4;
@@ -518,7 +523,7 @@ static int row_sm_count() {
 
 template <typename TA, int V>
 static int ln_fwd_launch(const float* x, const float* shift, const float* scale, int64_t ld_mod, int rpg, void* out,
-                         float* mean, float* rstd, int M, int D, float eps, cudaStream_t st) {
+                         int64_t ld_out, float* mean, float* rstd, int M, int D, float eps, cudaStream_t st) {
   auto kernel = ln_modulate_fwd_kernel<TA, V>;
   const int smem = (kLnWarps * kLnStages + 2) * D * 4;
   static int configured = 0;
@@ -530,16 +535,16 @@ static int ln_fwd_launch(const float* x, const float* shift, const float* scale,
   // grid covers every SM at least twice
   int rows = 32;
   while (rows > 1 && (rpg % rows != 0 || ceil_div(M, rows) < 2 * row_sm_count())) rows >>= 1;
-  kernel<<<ceil_div(M, rows), kLnWarps * 32, smem, st>>>(x, shift, scale, ld_mod, rpg, rows, (TA*)out, mean, rstd, M, D, eps);
+  kernel<<<ceil_div(M, rows), kLnWarps * 32, smem, st>>>(x, shift, scale, ld_mod, rpg, rows, (TA*)out, ld_out, mean, rstd, M, D, eps);
   REED_LAUNCH_CHECK();
   return 0;
 }
 
 template <typename TA>
 static int ln_fwd_dispatch(const float* x, const float* shift, const float* scale, int64_t ld_mod, int rpg, void* out,
-                           float* mean, float* rstd, int M, int D, float eps, cudaStream_t st) {
+                           int64_t ld_out, float* mean, float* rstd, int M, int D, float eps, cudaStream_t st) {
   int nv = ceil_div(D, 128);
-#define LN_FWD(V) return ln_fwd_launch<TA, V>(x, shift, scale, ld_mod, rpg, out, mean, rstd, M, D, eps, st)
+#define LN_FWD(V) return ln_fwd_launch<TA, V>(x, shift, scale, ld_mod, rpg, out, ld_out, mean, rstd, M, D, eps, st)
   if (nv <= 4) LN_FWD(4); else if (nv <= 9) LN_FWD(9); else if (nv <= 12) LN_FWD(12); else LN_FWD(16);
 #undef LN_FWD
 }
@@ -716,16 +721,17 @@ using namespace reed;
   REED_REQUIRE((rpg) > 0 && (M) % (rpg) == 0, "M=%d not a multiple of rows_per_group=%d", (int)(M), (int)(rpg))
 
 extern "C" int reed_ln_modulate_fwd(const void* x, const void* shift, const void* scale, int64_t ld_mod,
-                                    int rows_per_group, void* out, int act_dtype, void* mean, void* rstd, int M, int D,
-                                    float eps, void* stream) {
+                                    int rows_per_group, void* out, int64_t ld_out, int act_dtype, void* mean, void* rstd,
+                                    int M, int D, float eps, void* stream) {
   ROW_ARGS_OK(M, D, rows_per_group);
+  REED_REQUIRE(ld_out >= D && ld_out % 8 == 0, "ln_modulate_fwd: output pitch must be >= D and a multiple of 8 elements");
   if (M == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
   if (act_dtype == kBF16)
     return ln_fwd_dispatch<bf16>((const float*)x, (const float*)shift, (const float*)scale, ld_mod, rows_per_group, out,
-                                 (float*)mean, (float*)rstd, M, D, eps, st);
+                                 ld_out, (float*)mean, (float*)rstd, M, D, eps, st);
   return ln_fwd_dispatch<float>((const float*)x, (const float*)shift, (const float*)scale, ld_mod, rows_per_group, out,
-                                (float*)mean, (float*)rstd, M, D, eps, st);
+                                ld_out, (float*)mean, (float*)rstd, M, D, eps, st);
 }
 
 #define ROW_MOD_OK(ld) REED_REQUIRE((ld) % 4 == 0, "row kernels need modulation rows with a pitch that is a multiple of 4 floats")

@@ -171,6 +171,9 @@ void gemm_tcgen05_force_bn(int bn) { g_force_bn = bn; }
 int gemm_tcgen05(const void* A, int64_t lda, int a_mn, const void* B, int64_t ldb, int b_mn, void* D, int64_t ldd,
                  int d_dtype, int M, int N, int K, const EpiParams& ep, cudaStream_t st) {
   // the split mode needs an output that tolerates fp32 atomics: no epilogue, no bias, fp32 D (the weight gradients)
+  REED_REQUIRE(ep.bias_grad == nullptr || (ep.kind == kEpiNone && d_dtype == kF32 && ep.bias == nullptr && ep.n_store > 0 &&
+                                          ep.n_store < N && ep.n_store % 4 == 0),
+               "gemm_tcgen05: a bias-gradient column needs a plain fp32 weight-gradient GEMM");
   const bool sk_ok = ep.kind == kEpiNone && d_dtype == kF32 && ep.bias == nullptr && ep.out2 == nullptr;
   const GemmPlan p = plan_gemm(M, N, K, b_mn, sk_ok, g_force_cg, g_force_bn);
   if (p.stream_k > 1 && !ep.accumulate) {
@@ -180,7 +183,8 @@ int gemm_tcgen05(const void* A, int64_t lda, int a_mn, const void* B, int64_t ld
     const int first = (tiles / workers) * workers;
     const int row0 = (first / tiles_n) * 128 * p.cg;
     if (row0 < M)
-      REED_CHECK_CUDA(cudaMemset2DAsync((char*)D + (size_t)row0 * ldd * 4, (size_t)ldd * 4, 0, (size_t)N * 4, (size_t)(M - row0), st));
+      REED_CHECK_CUDA(cudaMemset2DAsync((char*)D + (size_t)row0 * ldd * 4, (size_t)ldd * 4, 0,
+                                        (size_t)(ep.bias_grad != nullptr ? ep.n_store : N) * 4, (size_t)(M - row0), st));
   }
 
   CUtensorMap ma, mb;

@@ -163,9 +163,10 @@ __device__ __forceinline__ void epilogue_tile(const EpiParams& ep, TD* __restric
     g_uniform = g_first == last || row_base >= M;
   }
 
+  const int n_lim = ep.bias_grad != nullptr ? ep.n_store : N;    // columns that exist in D
   auto prefetch = [&](int c0) {
     const int col = n0 + c0 + cc;
-    if (col < N) {
+    if (col < n_lim) {
       if (ep.bias != nullptr) b4 = __ldg(reinterpret_cast<const float4*>(ep.bias + col));
       if constexpr (KIND == kEpiGateRes) {
         if (g_uniform && row_base < M) g4 = __ldg(reinterpret_cast<const float4*>(ep.gate + (int64_t)g_first * ep.ld_gate + col));
@@ -213,6 +214,12 @@ __device__ __forceinline__ void epilogue_tile(const EpiParams& ep, TD* __restric
     auto row_op = [&](int it) {
       const int row = row_base + it * 4 + rsub;
       const float4 f = fr[it];
+      if constexpr (KIND == kEpiNone || KIND == kEpiAccum || KIND == kEpiAtomic) {
+        if (ep.bias_grad != nullptr && col >= ep.n_store) {       // the ones column of B: column sums of A
+          if (col == ep.n_store) atomicAdd(ep.bias_grad + row, f.x);
+          return;
+        }
+      }
       F4 acc{{f.x + b4.x, f.y + b4.y, f.z + b4.z, f.w + b4.w}};
       TD* dptr = D + (int64_t)row * ldd + col;
       if constexpr (KIND == kEpiNone) {
@@ -811,14 +818,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     if (ep.kind == kEpiGateRes) { aux = (const char*)ep.aux; aux_pitch = ep.ld_aux * 4; }
     else if (ep.kind == kEpiDGelu || ep.kind == kEpiDSilu) { aux = (const char*)ep.aux; aux_pitch = ep.ld_aux * 2; aux_esz = 2; }
     else if (ep.kind == kEpiNone && ep.accumulate && sizeof(TD) == 4) { aux = (const char*)D; aux_pitch = ldd * 4; }
+    const int n_cols = ep.bias_grad != nullptr ? ep.n_store : N;   // columns that exist in D
     Seg sg, nx;
     bool have = sched.next(sg);
     if (have && !sg.atomic)
-      epilogue_l2_prefetch<BN>(aux, aux_pitch, aux_esz, M, N, (sg.tile / tiles_n) * BMT + (int)rank * BM, (sg.tile % tiles_n) * BN, q, half, lane);
+      epilogue_l2_prefetch<BN>(aux, aux_pitch, aux_esz, M, n_cols, (sg.tile / tiles_n) * BMT + (int)rank * BM, (sg.tile % tiles_n) * BN, q, half, lane);
     while (have) {
       const bool have_next = sched.next(nx);
       if (have_next && !nx.atomic)
-        epilogue_l2_prefetch<BN>(aux, aux_pitch, aux_esz, M, N, (nx.tile / tiles_n) * BMT + (int)rank * BM, (nx.tile % tiles_n) * BN, q, half, lane);
+        epilogue_l2_prefetch<BN>(aux, aux_pitch, aux_esz, M, n_cols, (nx.tile / tiles_n) * BMT + (int)rank * BM, (nx.tile % tiles_n) * BN, q, half, lane);
       const int m0 = (sg.tile / tiles_n) * BMT + (int)rank * BM, n0 = (sg.tile % tiles_n) * BN;
       const uint32_t taddr = tmem_base + acc * BN + ((uint32_t)(q * 32) << 16);
 #define REED_EPI(KIND) epilogue_tile<KIND, BN, TD>(ep, D, ldd, M, N, m0, n0, taddr, st, q, half, lane, &tfull[acc], acc_phase)

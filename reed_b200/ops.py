@@ -22,6 +22,10 @@ EPI_NONE, EPI_GELU, EPI_SILU, EPI_GATE_RES, EPI_DGELU, EPI_DSILU = range(6)
 ACT_NONE, ACT_GELU, ACT_SILU = 0, 1, 2
 BACKEND_AUTO, BACKEND_SIMT, BACKEND_TENSOR, BACKEND_TENSOR_CG1, BACKEND_TENSOR_CG2 = 0, 1, 2, 3, 4
 
+import os as _os
+
+# profiling knob: 0 = bias gradients of qkv / fc1 by a separate column-sum pass instead of the ones-column GEMM
+_WGRAD_BIAS = _os.environ.get("REED_WGRAD_BIAS", "1") != "0"
 _gemm_backend = BACKEND_AUTO
 _attn_backend = BACKEND_AUTO
 launch_count = 0     # kernels launched through this module (bench.py reports it as gpu_launches)
@@ -142,15 +146,30 @@ def act_bwd(dy, h, act):
     return dx
 
 
-def ln_modulate_fwd(x, shift, scale, rows_per_group, act_dtype, eps=1e-6):
+def ln_modulate_fwd(x, shift, scale, rows_per_group, act_dtype, eps=1e-6, ones_col=False):
+    """ones_col (bf16 only): rows get spare elements with [1,0,...,0] at columns D..D+7 - the operand form wgrad_bias()
+    contracts against.  The pitch grows by 64 elements (128 bytes) so that rows stay 128-byte aligned for the TMA boxes.
+    Returns the [M, D] view; its storage is ``out._base``."""
     M, D = x.shape
-    out = torch.empty((M, D), device=x.device, dtype=act_dtype)
+    ones_col = ones_col and _WGRAD_BIAS and act_dtype == torch.bfloat16
+    ld_out = D + 64 if ones_col else D
+    buf = torch.empty((M, ld_out), device=x.device, dtype=act_dtype)
     mean = torch.empty((M,), device=x.device, dtype=torch.float32)
     rstd = torch.empty((M,), device=x.device, dtype=torch.float32)
     assert shift.stride(0) == scale.stride(0) and shift.stride(1) == 1 and scale.stride(1) == 1
-    _launch("reed_ln_modulate_fwd", _p(x), _p(shift), _p(scale), shift.stride(0), rows_per_group, _p(out),
+    _launch("reed_ln_modulate_fwd", _p(x), _p(shift), _p(scale), shift.stride(0), rows_per_group, _p(buf), ld_out,
             _code(act_dtype), _p(mean), _p(rstd), M, D, eps, _stream())
-    return out, mean, rstd
+    return (buf[:, :D] if ones_col else buf), mean, rstd
+
+
+def wgrad_bias(dy2d, x_ext, k_in, dw, db, accumulate):
+    """dW (+)= dy^T x and db += colsum(dy) in one GEMM; x_ext [tokens, >= K+8] carries the ones column at index K."""
+    tokens, n_out = dy2d.shape
+    assert x_ext.shape[1] >= k_in + 8
+    assert dy2d.dtype == x_ext.dtype == torch.bfloat16 and dy2d.stride(1) == 1 and x_ext.stride(1) == 1
+    assert dw.shape == (n_out, k_in) and dw.stride(1) == 1 and db.numel() == n_out and db.is_contiguous()
+    _launch("reed_gemm_wgrad_bias", _p(dy2d), dy2d.stride(0), _p(x_ext), x_ext.stride(0), _p(dw), dw.stride(0), _p(db),
+            n_out, k_in, tokens, int(accumulate), _stream())
 
 
 def ln_modulate_bwd(dout, x, mean, rstd, scale, rows_per_group, dres, dshift, dscale):
@@ -227,6 +246,23 @@ def _weight_grad(p, dy2d, x2d):
         gemm(dy2d, x2d, a_mn=True, b_mn=True, out=main.view(dy2d.shape[1], x2d.shape[1]), accumulate=acc)
         return None
     return gemm(dy2d, x2d, a_mn=True, b_mn=True, out_dtype=torch.float32).view(p.shape)
+
+
+def _weight_and_bias_grad(w, b, dy2d, x2d, x_ext):
+    """Gradients of y = x W^T + b.  With a trainer's flat gradient storage and an activation matrix that carries the ones
+    column, both come out of one GEMM; otherwise the weight-gradient GEMM plus a column-sum pass."""
+    wmain, wacc = (getattr(w, "_reed_main_grad", None), False)
+    bmain = getattr(b, "_reed_main_grad", None) if b is not None else None
+    if x_ext is not None and wmain is not None and bmain is not None and dy2d.dtype == torch.bfloat16:
+        wmain, wacc = _grad_target(w)
+        bmain, bacc = _grad_target(b)
+        if not bacc:
+            _zero_fresh(b, bmain)
+        wgrad_bias(dy2d, x_ext, x2d.shape[1], wmain.view(dy2d.shape[1], x2d.shape[1]), bmain, wacc)
+        return None, None
+    db = _bias_grad(b, dy2d) if b is not None else None
+    dw = _weight_grad(w, dy2d, x2d)
+    return dw, db
 
 
 def _zero_fresh(p, main):
@@ -419,7 +455,7 @@ class SiTBlockFn(torch.autograd.Function):
 
         mod = gemm(c_act, W(w_ada), out_dtype=torch.float32, bias=b_ada.detach())
         sh_a, sc_a, g_a, sh_m, sc_m, g_m = (mod[:, i * D:(i + 1) * D] for i in range(6))
-        xm1, mean1, rstd1 = ln_modulate_fwd(x0, sh_a, sc_a, T, act_dtype)
+        xm1, mean1, rstd1 = ln_modulate_fwd(x0, sh_a, sc_a, T, act_dtype, ones_col=True)
         qkv_raw = gemm(xm1, W(w_qkv), out_dtype=act_dtype, bias=b_qkv.detach())
         qk_stats = None
         qkv = qkv_raw
@@ -430,14 +466,16 @@ class SiTBlockFn(torch.autograd.Function):
         y1 = torch.empty((M, D), device=x.device, dtype=act_dtype)
         x1 = gemm(o, W(w_proj), out_dtype=torch.float32, bias=b_proj.detach(), epilogue=EPI_GATE_RES, aux=x0, gate=g_a,
                   rows_per_group=T, out2=y1)
-        xm2, mean2, rstd2 = ln_modulate_fwd(x1, sh_m, sc_m, T, act_dtype)
+        xm2, mean2, rstd2 = ln_modulate_fwd(x1, sh_m, sc_m, T, act_dtype, ones_col=True)
         h = torch.empty((M, w_fc1.shape[0]), device=x.device, dtype=act_dtype)
         a = gemm(xm2, W(w_fc1), out_dtype=act_dtype, bias=b_fc1.detach(), epilogue=EPI_GELU, out2=h)
         y2 = torch.empty((M, D), device=x.device, dtype=act_dtype)
         x2 = gemm(a, W(w_fc2), out_dtype=torch.float32, bias=b_fc2.detach(), epilogue=EPI_GATE_RES, aux=x1, gate=g_m,
                   rows_per_group=T, out2=y2)
 
-        ctx.save_for_backward(x0, c_act, mod, mean1, rstd1, xm1, qkv, o, lse, y1, x1, mean2, rstd2, xm2, h, a, y2,
+        # xm1 / xm2 are [M, D] views of wider rows (ones column): save the storage, re-slice in backward
+        ctx.save_for_backward(x0, c_act, mod, mean1, rstd1, xm1._base if xm1._base is not None else xm1, qkv, o, lse, y1,
+                              x1, mean2, rstd2, xm2._base if xm2._base is not None else xm2, h, a, y2,
                               qkv_raw if qk_stats is not None else None, qk_stats)
         ctx.params = (w_ada, b_ada, w_qkv, b_qkv, w_proj, b_proj, w_fc1, b_fc1, w_fc2, b_fc2)
         ctx.qk_params = (qn_w, qn_b, kn_w, kn_b)
@@ -449,10 +487,13 @@ class SiTBlockFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dx2):
-        (x0, c_act, mod, mean1, rstd1, xm1, qkv, o, lse, y1, x1, mean2, rstd2, xm2, h, a, y2, qkv_raw,
+        (x0, c_act, mod, mean1, rstd1, xm1s, qkv, o, lse, y1, x1, mean2, rstd2, xm2s, h, a, y2, qkv_raw,
          qk_stats) = ctx.saved_tensors
         w_ada, b_ada, w_qkv, b_qkv, w_proj, b_proj, w_fc1, b_fc1, w_fc2, b_fc2 = ctx.params
         B, T, D, H, hd = ctx.dims
+        xm1_ext = xm1s if xm1s.shape[1] > D else None
+        xm2_ext = xm2s if xm2s.shape[1] > D else None
+        xm1, xm2 = xm1s[:, :D], xm2s[:, :D]
         M = B * T
         act_dtype = ctx.act_dtype
         W = lambda p: weight_for(p, act_dtype)
@@ -477,8 +518,7 @@ class SiTBlockFn(torch.autograd.Function):
         dy2 = gate_bwd(dx2, y2, g_m, T, dg_m, db2_buf)
         dw2 = _weight_grad(w_fc2, dy2, a)
         dh = gemm(dy2, W(w_fc2), b_mn=True, out_dtype=act_dtype, epilogue=EPI_DGELU, aux=h)
-        db1 = _bias_grad(b_fc1, dh)
-        dw1 = _weight_grad(w_fc1, dh, xm2)
+        dw1, db1 = _weight_and_bias_grad(w_fc1, b_fc1, dh, xm2, xm2_ext)
         dxm2 = gemm(dh, W(w_fc1), b_mn=True, out_dtype=act_dtype)
         # ---- attention branch:  x1 = x0 + g_a * (attn(xm1) Wp^T + bp); its gate backward rides on the LN backward
         dbp_buf, dbp = bias_buffer(b_proj)
@@ -497,8 +537,7 @@ class SiTBlockFn(torch.autograd.Function):
             dqkv = qk_norm_bwd(dqkv, qkv_raw, qk_stats, qn_w.detach().float(), kn_w.detach().float(), bufs[0], bufs[1],
                                bufs[2], bufs[3], M, H, hd)
             qk_grads = tuple(rets)
-        dbqkv = _bias_grad(b_qkv, dqkv)
-        dwqkv = _weight_grad(w_qkv, dqkv, xm1)
+        dwqkv, dbqkv = _weight_and_bias_grad(w_qkv, b_qkv, dqkv, xm1, xm1_ext)
         dxm1 = gemm(dqkv, W(w_qkv), b_mn=True, out_dtype=act_dtype)
         dx0 = ln_modulate_bwd(dxm1, x0, mean1, rstd1, sc_a, T, dx1, dsh_a, dsc_a)
 

@@ -193,6 +193,33 @@ def test_gemm_stream_k_wgrad(ops, shape, cg):
     assert _rel(big[:, :N], ref) < 2e-5 and float(big[:, N:].abs().max()) == 0.0
 
 
+@pytest.mark.parametrize("shape", [(1152, 1152, 4096), (3456, 1152, 2048), (384, 256, 1024), (512, 128, 48)])
+def test_gemm_wgrad_with_bias_column(ops, shape):
+    """dW = dy^T x and db = colsum(dy) from ONE GEMM: LN+modulate leaves a ones column behind the activation rows and the
+    weight-gradient GEMM contracts against it (last shape: too few tokens for the tensor path -> GEMM + column sums)."""
+    n_out, k_in, tokens = shape
+    T = 16
+    x = _rand(tokens, k_in, seed=21)
+    mod = _rand(tokens // T, 2 * k_in, scale=0.3, seed=22)
+    xm, _, _ = ops.ln_modulate_fwd(x, mod[:, :k_in], mod[:, k_in:], T, torch.bfloat16, ones_col=True)
+    ext = xm._base
+    assert ext.shape[1] >= k_in + 8 and xm.stride(0) == ext.shape[1] and (ext.shape[1] * 2) % 128 == 0
+    torch.cuda.synchronize()
+    assert bool((ext[:, k_in] == 1).all()) and bool((ext[:, k_in + 1:k_in + 8] == 0).all())
+    dy = _rand(tokens, n_out, dtype=torch.bfloat16, scale=tokens ** -0.5, seed=23)
+    dw = torch.full((n_out, k_in), 3.0, device=DEV)        # stale contents must be overwritten
+    db = torch.zeros(n_out, device=DEV)
+    ops.wgrad_bias(dy, ext, k_in, dw, db, accumulate=False)
+    torch.cuda.synchronize()
+    ref_w = dy.float().t() @ xm.float()
+    ref_b = dy.float().sum(0)
+    assert _rel(dw, ref_w) < 2e-5, shape
+    assert _rel(db, ref_b) < 2e-5, shape
+    ops.wgrad_bias(dy, ext, k_in, dw, db, accumulate=True)       # gradient accumulation: both add up
+    torch.cuda.synchronize()
+    assert _rel(dw, 2 * ref_w) < 2e-5 and _rel(db, 2 * ref_b) < 2e-5
+
+
 def test_gemm_simt_skinny_and_split_k(ops):
     ops.set_backends()
     # final-layer shapes: N = 16 forward, and its wgrad with a long reduction (split-K path)
