@@ -352,14 +352,19 @@ __device__ __forceinline__ void epilogue_loop_tma(const EpiParams& ep, const Epi
     const int nvalid = width >= BN ? NCH : (width + kStageCols - 1) / kStageCols;
     return nvalid > half ? (nvalid - half + 1) / 2 : 0;
   };
-  auto row0_of = [&](const Seg& sgm) { return (sgm.tile / tiles_n) * BMT + (int)rank * BM + q * 32; };
-  auto col0_of = [&](const Seg& sgm, int k) { return (sgm.tile % tiles_n) * BN + (half + 2 * k) * kStageCols; };
+  // tile -> first row of this warp / first column of the tile: one integer division per tile, not per chunk
+  struct Org { int row0, n0; };
+  auto org_of = [&](const Seg& sgm) {
+    const int tm = sgm.tile / tiles_n;
+    return Org{tm * BMT + (int)rank * BM + q * 32, (sgm.tile - tm * tiles_n) * BN};
+  };
+  auto col0_at = [&](const Org& o, int k) { return o.n0 + (half + 2 * k) * kStageCols; };
 
   int acc = 0;
   uint32_t acc_phase = 0;
   // bias of a chunk: lane l holds bias[col0 + l], fetched one chunk ahead (also across tiles), broadcast by shuffles
-  auto load_bias = [&](const Seg& ts, int k) {
-    const int c = col0_of(ts, k) + lane;
+  auto load_bias = [&](const Org& o, int k) {
+    const int c = col0_at(o, k) + lane;
     return (ep.bias != nullptr && c < N) ? __ldg(ep.bias + c) : 0.f;
   };
   float b_next = 0.f;
@@ -367,15 +372,17 @@ __device__ __forceinline__ void epilogue_loop_tma(const EpiParams& ep, const Epi
   int issued = 0;       // operand requests made, counted from the current tile's first chunk (may run into the next tile)
   Seg sg, nx;
   bool have = sched.next(sg);
-  if (have && my_chunks(sg) > 0) b_next = load_bias(sg, 0);
+  Org og = have ? org_of(sg) : Org{0, 0}, ogn = og;
+  if (have && my_chunks(sg) > 0) b_next = load_bias(og, 0);
   while (have) {
     const bool have_next = sched.next(nx);
+    if (have_next) ogn = org_of(nx);
     const int cnt = my_chunks(sg), cntn = have_next ? my_chunks(nx) : 0;
-    const int row0 = row0_of(sg);
+    const int row0 = og.row0;
     if constexpr (E::kSlots > 0) {   // the next tile's operand rows -> L2, so the TMA requests above hit there
       if (have_next)
         epilogue_l2_prefetch<BN>((const char*)ep.aux, ep.ld_aux * (E::kAuxF32 ? 4 : 2), E::kAuxF32 ? 4 : 2, M, N,
-                                 (nx.tile / tiles_n) * BMT + (int)rank * BM, (nx.tile % tiles_n) * BN, q, half, lane);
+                                 ogn.row0 - q * 32, ogn.n0, q, half, lane);
     }
     const uint32_t taddr = tmem_base + acc * BN + ((uint32_t)(q * 32) << 16);
     // request operand boxes up to kLook chunks ahead of chunk p (lane 0 issues; mbarrier per ring slot)
@@ -383,7 +390,7 @@ __device__ __forceinline__ void epilogue_loop_tma(const EpiParams& ep, const Epi
       if constexpr (E::kSlots > 0) {
         while (issued < p + E::kLook + 1 && issued < cnt + cntn) {
           const bool in_next = issued >= cnt;
-          const Seg& ts = in_next ? nx : sg;
+          const Org& to = in_next ? ogn : og;
           const int k = in_next ? issued - cnt : issued;
           const int slot = (gbase + issued) % E::kSlots;
           if (lane == 0) {
@@ -391,7 +398,7 @@ __device__ __forceinline__ void epilogue_loop_tma(const EpiParams& ep, const Epi
             if constexpr (E::kAuxF32) bulk_wait_read<0>();
             const uint32_t bar = smem_u32(&auxbar[slot]);
             mbar_expect_tx_u32(bar, 32 * kStageCols * (E::kAuxF32 ? 4 : 2));
-            tma_load_2d_u32(&em.aux, bar, wbuf + slot * E::kSlotBytes, col0_of(ts, k), row0_of(ts));
+            tma_load_2d_u32(&em.aux, bar, wbuf + slot * E::kSlotBytes, col0_at(to, k), to.row0);
           }
           ++issued;
         }
@@ -403,10 +410,10 @@ __device__ __forceinline__ void epilogue_loop_tma(const EpiParams& ep, const Epi
 #pragma unroll 1
     for (int p = 0; p < cnt; ++p) {
       const int G = gbase + p;                      // ring position
-      const int col0 = col0_of(sg, p);
+      const int col0 = col0_at(og, p);
       const float b_cur = b_next;
-      if (p + 1 < cnt) b_next = load_bias(sg, p + 1);
-      else if (cntn > 0) b_next = load_bias(nx, 0);
+      if (p + 1 < cnt) b_next = load_bias(og, p + 1);
+      else if (cntn > 0) b_next = load_bias(ogn, 0);
       float v[32];
       tmem_ld32(taddr + (half + 2 * p) * kStageCols, v);
       if (ep.bias != nullptr) {
@@ -476,6 +483,7 @@ __device__ __forceinline__ void epilogue_loop_tma(const EpiParams& ep, const Epi
     gbase += cnt;
     issued -= cnt;
     sg = nx;
+    og = ogn;
     have = have_next;
   }
   if (lane == 0) bulk_wait_all();   // the boxes must outlive their stores

@@ -198,15 +198,21 @@ __device__ __forceinline__ float tanh_fast(float x) {
   asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// tanh-GELU with the constants folded: arg = x (k0 + k0 k1 x^2); 6 / 11 fp32 operations per element
 __device__ __forceinline__ float gelu_fast(float x) {
-  const float k0 = 0.7978845608028654f, k1 = 0.044715f;
-  return 0.5f * x * (1.f + tanh_fast(k0 * (x + k1 * x * x * x)));
+  const float k0 = 0.7978845608028654f, k0k1 = 0.7978845608028654f * 0.044715f;
+  const float u = x * x;
+  const float th = tanh_fast(x * fmaf(k0k1, u, k0));
+  const float hx = 0.5f * x;
+  return fmaf(hx, th, hx);
 }
 __device__ __forceinline__ float gelu_grad_fast(float x) {
-  const float k0 = 0.7978845608028654f, k1 = 0.044715f;
-  const float x2 = x * x;
-  const float th = tanh_fast(k0 * (x + k1 * x * x2));
-  return 0.5f * (1.f + th) + 0.5f * x * (1.f - th * th) * (k0 * (1.f + 3.f * k1 * x2));
+  const float k0 = 0.7978845608028654f, k0k1 = 0.7978845608028654f * 0.044715f;
+  const float u = x * x;
+  const float th = tanh_fast(x * fmaf(k0k1, u, k0));
+  // 0.5 (1 + th) + 0.5 x (1 - th^2) (k0 + 3 k0 k1 x^2)
+  const float e = (0.5f * x) * fmaf(3.f * k0k1, u, k0);
+  return fmaf(0.5f, th, fmaf(e, fmaf(-th, th, 1.f), 0.5f));
 }
 __device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
 __device__ __forceinline__ float silu_fast(float x) { return x * sigmoid_fast(x); }
