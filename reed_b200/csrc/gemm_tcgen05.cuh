@@ -373,11 +373,15 @@ __device__ __forceinline__ void epilogue_loop_tma(const EpiParams& ep, const Epi
   Seg sg, nx;
   bool have = sched.next(sg);
   Org og = have ? org_of(sg) : Org{0, 0}, ogn = og;
-  if (have && my_chunks(sg) > 0) b_next = load_bias(og, 0);
+  bool b_ready = false;   // b_next already holds the bias of the coming tile's first chunk
   while (have) {
     const bool have_next = sched.next(nx);
     if (have_next) ogn = org_of(nx);
     const int cnt = my_chunks(sg), cntn = have_next ? my_chunks(nx) : 0;
+    // (a tile may hold no chunk of this warp - a last column tile at most 32 columns wide - so the look-ahead of the
+    // previous tile's last chunk cannot be relied on)
+    if (cnt > 0 && !b_ready) b_next = load_bias(og, 0);
+    b_ready = false;
     const int row0 = og.row0;
     if constexpr (E::kSlots > 0) {   // the next tile's operand rows -> L2, so the TMA requests above hit there
       if (have_next)
@@ -413,7 +417,7 @@ __device__ __forceinline__ void epilogue_loop_tma(const EpiParams& ep, const Epi
       const int col0 = col0_at(og, p);
       const float b_cur = b_next;
       if (p + 1 < cnt) b_next = load_bias(og, p + 1);
-      else if (cntn > 0) b_next = load_bias(ogn, 0);
+      else if (cntn > 0) { b_next = load_bias(ogn, 0); b_ready = true; }
       float v[32];
       tmem_ld32(taddr + (half + 2 * p) * kStageCols, v);
       if (ep.bias != nullptr) {
@@ -536,10 +540,12 @@ __device__ __forceinline__ void epilogue_loop_tma_gateres(const EpiParams& ep, c
   int gbase = 0, issued = 0;
   Seg sg, nx;
   bool have = sched.next(sg);
-  if (have && my_chunks(sg) > 0) bg_next = load_bg(sg, 0);
+  bool bg_ready = false;
   while (have) {
     const bool have_next = sched.next(nx);
     const int cnt = my_chunks(sg), cntn = have_next ? my_chunks(nx) : 0;
+    if (cnt > 0 && !bg_ready) bg_next = load_bg(sg, 0);
+    bg_ready = false;
     const int row0 = row0_of(sg);
     if (have_next)
       epilogue_l2_prefetch<BN>((const char*)ep.aux, ep.ld_aux * 4, 4, M, N, (nx.tile / tiles_n) * BMT + (int)rank * BM,
@@ -569,7 +575,7 @@ __device__ __forceinline__ void epilogue_loop_tma_gateres(const EpiParams& ep, c
       const int col0 = col0_of(sg, p);
       const float bg = bg_next;
       if (p + 1 < cnt) bg_next = load_bg(sg, p + 1);
-      else if (cntn > 0) bg_next = load_bg(nx, 0);
+      else if (cntn > 0) { bg_next = load_bg(nx, 0); bg_ready = true; }
       float v[16];
       tmem_ld16(taddr + (half + 2 * p) * W, v);
       top_up(p);
