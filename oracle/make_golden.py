@@ -181,8 +181,39 @@ def train_glue_case(ref_sit, ref_loss, ns, spec, state_seed, steps=3):
                 posterior=dict(moments=moments, noise=post_noise, out=post))
 
 
+def curriculum_case():
+    """train.py:363-385 executed from the reference source (the three statements that open the
+    ``with accelerator.accumulate(model)`` block) over a grid of steps and schedule arguments."""
+    import itertools
+    import types
+    import numpy as np
+    src = open(os.path.join(REF, "train.py")).read()
+    body = None
+    for node in ast.walk(ast.parse(src)):
+        if isinstance(node, ast.With) and "accumulate" in ast.get_source_segment(src, node.items[0].context_expr):
+            body = node.body[:3]
+    assert body is not None and [type(s).__name__ for s in body] == ["If", "Assign", "If"]
+    code = compile(ast.Module(body, []), "train.py", "exec")
+    cases = []
+    grids = dict(repa_weight_decay=["constant", "linear", "cosine"], diffusion_decay=["constant", "linear", "cosine"],
+                 start_diffusion_steps=[0, 300], diffusion_warm_up_steps=[50, 1000])
+    for combo in itertools.product(*grids.values()):
+        kw = dict(zip(grids.keys(), combo), repa_steps=4000, max_train_steps=5000)
+        for step in (0, 1, 49, 50, 299, 300, 349, 350, 999, 1000, 1299, 1300, 2500, 3999, 4000, 4999, 5000):
+            ns = {"args": types.SimpleNamespace(**kw), "global_step": step, "np": np}
+            exec(code, ns)
+            cases.append(dict(kw, global_step=step, diffusion=float(ns["_diffusion_loss_decay"]),
+                              repa=float(ns["_repa_weight_decay"])))
+    return cases
+
+
 def main():
     from .sit_oracle import ArchSpec
+    if "--only-curriculum" in sys.argv:
+        _import_reference()
+        torch.save(curriculum_case(), os.path.join(OUT, "curriculum.pt"))
+        print("curriculum.pt", os.path.getsize(os.path.join(OUT, "curriculum.pt")))
+        return
     torch.set_num_threads(8)
     ref_sit, ref_loss, ref_samplers, ns = _import_reference()
     os.makedirs(OUT, exist_ok=True)
@@ -213,6 +244,7 @@ def main():
     _, init_b = init_case(ref_sit, "SiT-B/2", seed=0)
     torch.save(init_b, os.path.join(OUT, "init_b2.pt"))
     torch.save(train_glue_case(ref_sit, ref_loss, ns, spec_t, state_seed=21), os.path.join(OUT, "train_glue.pt"))
+    torch.save(curriculum_case(), os.path.join(OUT, "curriculum.pt"))
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

@@ -51,3 +51,34 @@ def adamw_ema_step(params, grads, exp_avg, exp_avg_sq, ema, step, *, lr=1e-4, be
                 p.addcdiv_(exp_avg[name], denom, value=-lr / bc1)
             ema[name].mul_(ema_decay).add_(p, alpha=1 - ema_decay)
     return norm
+
+
+def curriculum(global_step, *, repa_weight_decay="constant", repa_steps=400000, start_diffusion_steps=0,
+               diffusion_warm_up_steps=50000, diffusion_decay="constant", max_train_steps=400000):
+    """(diffusion_loss_decay, repa_weight_decay) of train.py:363-385 for one step, numpy arithmetic as there.
+
+    The cosine diffusion decay keeps the reference's operator precedence (``/ max_train_steps - top_steps``).
+    """
+    import numpy as np
+    if repa_weight_decay == "constant":
+        repa = 1.0
+    elif repa_weight_decay == "linear":
+        repa = max(1.0 - global_step / repa_steps, 0.)
+    elif repa_weight_decay == "cosine":
+        repa = max((1.0 + np.cos(np.pi * global_step / repa_steps)) / 2, 0.)
+    else:
+        raise NotImplementedError
+    top = diffusion_warm_up_steps + start_diffusion_steps
+    if global_step < start_diffusion_steps:
+        diff = 0.0
+    elif global_step < top:
+        diff = (global_step - start_diffusion_steps) / diffusion_warm_up_steps
+    elif diffusion_decay == "constant":
+        diff = 1.0
+    elif diffusion_decay == "linear":
+        diff = 1.0 - (global_step - top) / (max_train_steps - top)
+    elif diffusion_decay == "cosine":
+        diff = (1.0 + np.cos(np.pi * (global_step - top) / max_train_steps - top)) / 2
+    else:
+        raise NotImplementedError
+    return float(diff), float(repa)
