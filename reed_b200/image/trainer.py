@@ -262,6 +262,74 @@ class ReedTrainer:
         """Global gradient norm of the last step (device scalar, after the all-reduce average)."""
         return (self._norm_sq.sqrt() * self.reducer.grad_scale).float()
 
+    # -- checkpoints in the reference's format (train.py:280-289 resume, 418-429 save) ---------------------------
+    # {"model": state_dict, "ema": state_dict, "opt": torch.optim.AdamW state_dict, "args": ..., "steps": int}: a file
+    # written here resumes under the reference's train.py / loads in its generate.py (ckpt['ema']), and the reverse.
+    def _param_slots(self):
+        """[(name, param, bucket or None, offset)] in ``model.parameters()`` order = AdamW's parameter indices."""
+        where = {}
+        for b in self.state.buckets:
+            for name, off in zip(b.names, b.offsets):
+                where[name] = (b, off)
+        return [(name, p) + where.get(name, (None, 0)) for name, p in self.model.named_parameters()]
+
+    def checkpoint(self, args=None, steps: Optional[int] = None) -> dict:
+        """Snapshot as the dict the reference passes to ``torch.save`` (train.py:420-426).  Tensors are copies: the
+        live parameters are views of the flat buckets, and ``torch.save`` of a view would write the whole bucket."""
+        def copied(sd):
+            return type(sd)((k, v.detach().clone()) for k, v in sd.items())
+        groups = torch.optim.AdamW(self.model.parameters(), lr=self.lr, betas=tuple(self.betas), eps=self.eps,
+                                   weight_decay=self.weight_decay).state_dict()["param_groups"]
+        opt_state = {}
+        if self.step_count > 0:
+            for idx, (name, p, b, off) in enumerate(self._param_slots()):
+                if b is None:                       # frozen (pos_embed): AdamW never creates state for it
+                    continue
+                n = p.numel()
+                opt_state[idx] = {"step": torch.tensor(float(self.step_count)),
+                                  "exp_avg": b.exp_avg[off:off + n].view(p.shape).clone(),
+                                  "exp_avg_sq": b.exp_avg_sq[off:off + n].view(p.shape).clone()}
+        return {"model": copied(self.model.state_dict()),
+                "ema": copied(self.ema.state_dict()) if self.ema is not None else None,
+                "opt": {"state": opt_state, "param_groups": groups},
+                "args": args, "steps": self.step_count if steps is None else steps}
+
+    def load_checkpoint(self, ckpt: dict, strict: bool = True) -> int:
+        """Resume from a checkpoint dict (this trainer's or the reference's, train.py:281-289).  Returns ckpt['steps']."""
+        self.model.load_state_dict(ckpt["model"], strict=strict)         # in-place copies: the flat views stay in place
+        if self.ema is not None and ckpt.get("ema") is not None:
+            self.ema.load_state_dict(ckpt["ema"], strict=strict)
+        opt = ckpt.get("opt")
+        step = 0
+        slots = self._param_slots()
+        for b in self.state.buckets:
+            b.exp_avg.zero_()
+            b.exp_avg_sq.zero_()
+        if opt is not None:
+            group = opt["param_groups"][0]
+            if len(opt["param_groups"]) != 1 or len(group["params"]) != len(slots):
+                raise ValueError(f"optimizer state covers {sum(len(g['params']) for g in opt['param_groups'])} parameters in "
+                                 f"{len(opt['param_groups'])} group(s); this model has {len(slots)} in one group")
+            self.lr, self.betas, self.eps = group["lr"], tuple(group["betas"]), group["eps"]
+            self.weight_decay = group["weight_decay"]
+            for idx, st in opt["state"].items():
+                name, p, b, off = slots[group["params"].index(idx)]
+                if b is None:
+                    continue
+                n = p.numel()
+                b.exp_avg[off:off + n].view(p.shape).copy_(st["exp_avg"])
+                b.exp_avg_sq[off:off + n].view(p.shape).copy_(st["exp_avg_sq"])
+                step = max(step, int(float(st["step"])))
+        self.step_count = step
+        self._step_dev.fill_(step)
+        for b in self.state.buckets:                    # the bf16 GEMM operands follow the loaded masters
+            if b.shadow is not None:
+                b.shadow.copy_(b.param)
+            for p in b.params:
+                if getattr(p, "_reed_shadow", None) is not None:
+                    p._reed_shadow_version = p._version
+        return int(ckpt.get("steps", step))
+
     def train_step(self, images, labels, zs, diffusion_decay=1.0, repa_decay=1.0):
         self.state.begin_step()
         loss, out = self.compute_loss(images, labels, zs, diffusion_decay, repa_decay)
