@@ -139,6 +139,15 @@ int reed_sampler_step(const void* x_cur, const void* v, int model_dtype, const v
                       int path_type, double cfg, double t_cur, double dt, void* stream);
 int reed_sampler_cast(const void* x, void* x_model, int model_dtype, int64_t n, int dup, void* stream);
 
+/* VAE-posterior draw of the latent data path (train.py:84-91 sample_posterior with the per-channel latents_scale /
+ * latents_bias of train.py:226-231): out[b,c,:] = ((moments[b,c,:] + moments[b,C+c,:] * noise[b,c,:]) * scale[c]) + bias[c],
+ * every operation rounded separately (bit-identical to the reference's PyTorch kernel sequence for the same noise).
+ * moments fp32 [batch, 2*channels, hw]; noise, out fp32 [batch, channels, hw]; scale / bias: device fp32 [channels], or
+ * NULL to use the scalar arguments. */
+int reed_sample_posterior(const void* moments, const void* noise, const void* scale, const void* bias,
+                          float scale_scalar, float bias_scalar, void* out, int batch, int channels, int hw,
+                          void* stream);
+
 /* Optimizer tail over flat fp32 buffers (train.py:94-105 update_ema, 253-259 AdamW, 402-412 clip/step/EMA).
  * grad_sumsq: *out (double) += sum g^2.   adamw_ema: g *= grad_scale * min(1, max_norm/(grad_scale*sqrt(*norm_sq)+1e-6))
  * (norm_sq NULL = no clipping), torch.optim.AdamW update with 1-based `step`, ema = decay*ema + (1-decay)*p, and
