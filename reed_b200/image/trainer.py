@@ -159,13 +159,14 @@ class GradientReducer:
         self.state = state
         self.group = group
         self.world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+        self.enabled = True        # False while micro-batches of an accumulated step are still adding into the buckets
 
     @property
     def grad_scale(self):
         return 1.0 / self.world
 
     def launch(self, bucket: Bucket):
-        if self.world == 1 or bucket.work is not None:
+        if self.world == 1 or bucket.work is not None or not self.enabled:
             return
         bucket.work = dist.all_reduce(bucket.grad, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
 
@@ -336,6 +337,33 @@ class ReedTrainer:
         self._backward(loss)
         self.optimizer_step()
         return loss.detach(), out
+
+    def train_step_accumulated(self, micro_batches, diffusion_decay=1.0, repa_decay=1.0):
+        """One optimizer step over several micro-batches: ``accelerator.accumulate(model)`` with
+        ``--gradient-accumulation-steps k`` (train.py:151,362,401).  Every micro-batch's loss is divided by k before
+        backward (what ``accelerator.backward`` does), the weight-gradient kernels add into the flat buckets from the
+        second micro-batch on, and the bucket all-reduces start only in the last backward (DDP ``no_sync`` until then).
+        ``micro_batches``: sequence of ``(images, labels, zs)``.  Returns (mean loss, list of per-micro-batch dicts)."""
+        micro_batches = list(micro_batches)
+        k = len(micro_batches)
+        if k == 0:
+            raise ValueError("train_step_accumulated needs at least one micro-batch")
+        self.state.begin_step()
+        total, outs = 0.0, []
+        for i, (images, labels, zs) in enumerate(micro_batches):
+            loss, out = self.compute_loss(images, labels, zs, diffusion_decay, repa_decay)
+            outs.append(out)
+            total = total + loss.detach()
+            if i < k - 1:
+                self.reducer.enabled = False
+                try:
+                    (loss / k).backward()
+                finally:
+                    self.reducer.enabled = True
+            else:
+                self._backward(loss / k)
+        self.optimizer_step()
+        return total / k, outs
 
     # -- CUDA-graph replay of the whole step -----------------------------------------------------------------------
     # The step launches ~1100 kernels; enqueueing them from Python costs about as long as they run on a B200.  The

@@ -63,11 +63,16 @@ def _worker(rank, world, port, out):
         assert red.world == world and red.grad_scale == 1.0 / world
         for i, b in enumerate(st.buckets):
             b.grad.copy_(torch.arange(b.numel, dtype=torch.float32) * (rank + 1) + i)
+        # micro-batches of an accumulated step hold the all-reduce back (DDP no_sync): launch is a no-op while disabled
+        red.enabled = False
+        red.launch(st.bucket_of_block(2))
+        held = st.bucket_of_block(2).work is None
+        red.enabled = True
         # block buckets are launched early (as their backward completes), the rest in finish()
         red.launch(st.bucket_of_block(2))
         red.launch(st.bucket_of_block(2))        # idempotent
         red.finish()
-        ok = True
+        ok = held
         for i, b in enumerate(st.buckets):
             want = torch.arange(b.numel, dtype=torch.float32) * sum(r + 1 for r in range(world)) + i * world
             ok &= bool(torch.equal(b.grad, want))

@@ -1,0 +1,72 @@
+"""GPU tests of features added after round 1's GPU minutes were spent.  They are marked ``gpu_next`` (NOT ``gpu``): they
+have never run on a B200, so they stay out of the `-m gpu` suite until the first GPU call of round 2 has run them
+(`python -m pytest tests/test_zz_next_gpu.py -m gpu_next`), after which they move to ``gpu``."""
+import pytest
+import torch
+
+from oracle.fixtures import random_batch, random_state
+from oracle.sit_oracle import ArchSpec
+
+pytestmark = pytest.mark.gpu_next
+DEV = "cuda"
+
+
+def _tiny(precision, seed=11):
+    from reed_b200.image.loss import SILoss
+    from reed_b200.image.models.sit import SiT
+    from reed_b200.image.trainer import ReedTrainer
+    spec = ArchSpec(input_size=16, hidden_size=128, decoder_hidden_size=128, depth=2, num_heads=2, encoder_depth=1,
+                    z_dims=[64], projector_dim=128)
+    m = SiT(path_type="linear", use_cfg=True, input_size=16, hidden_size=128, decoder_hidden_size=128, depth=2, num_heads=2,
+            encoder_depth=1, z_dims=[64], z_types=["i"], projector_dim=128, num_classes=1000, fused_attn=True, qk_norm=False)
+    m.load_state_dict(random_state(spec, seed))
+    m = m.to(DEV).train()
+    return spec, ReedTrainer(m, SILoss(enc_names=["dinov2"], loss_weights={"dinov2": 1.0}), precision=precision)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_gradient_accumulation_averages_micro_batch_gradients(precision):
+    """train.py:362 `accelerator.accumulate`: the accumulated flat gradient of k micro-batches = mean of their gradients."""
+    spec, tr = _tiny(precision)
+    to_dev = lambda d: (d["x"].to(DEV), d["y"].to(DEV), [z.to(DEV) for z in d["zs"]])
+    micro = [to_dev(random_batch(spec, 4, 70 + i)) for i in range(3)]
+    singles = []
+    for seed, batch in zip((1, 2, 3), micro):
+        torch.manual_seed(seed)
+        tr.state.begin_step()
+        loss, _ = tr.compute_loss(*batch)
+        loss.backward()
+        tr.state.finish_backward()
+        singles.append([b.grad.clone() for b in tr.state.buckets])
+    want = [sum(gs) / 3 for gs in zip(*singles)]
+    seeds = iter((1, 2, 3))
+    plain_loss = tr.compute_loss
+
+    def seeded(*a, **k):
+        torch.manual_seed(next(seeds))
+        return plain_loss(*a, **k)
+
+    tr.compute_loss = seeded
+    tr.optimizer_step = lambda **k: None                      # keep the weights: look at the accumulated gradient only
+    loss, outs = tr.train_step_accumulated(micro)
+    assert len(outs) == 3 and torch.isfinite(loss)
+    for b, w in zip(tr.state.buckets, want):
+        err = float((b.grad - w).abs().max() / w.abs().max().clamp_min(1e-20))
+        assert err < (1e-5 if precision == "fp32" else 1e-2), (b.name, err)
+        assert float(torch.nn.functional.cosine_similarity(b.grad, w, dim=0)) > 0.9999
+
+
+def test_single_micro_batch_accumulated_step_equals_plain_step():
+    spec, a = _tiny("fp32")
+    _, b = _tiny("fp32")
+    batch = random_batch(spec, 4, 80)
+    dev = (batch["x"].to(DEV), batch["y"].to(DEV), [z.to(DEV) for z in batch["zs"]])
+    torch.manual_seed(4)
+    la, _ = a.train_step(*dev, diffusion_decay=0.8, repa_decay=0.6)
+    torch.manual_seed(4)
+    lb, _ = b.train_step_accumulated([dev], diffusion_decay=0.8, repa_decay=0.6)
+    assert abs(float(la) - float(lb)) <= 1e-6 * max(1.0, abs(float(la)))
+    for ba, bb in zip(a.state.buckets, b.state.buckets):
+        assert float((ba.param - bb.param).abs().max()) <= 2e-5
+        assert float((ba.ema - bb.ema).abs().max()) <= 2e-5
+    assert a.step_count == b.step_count == 1
