@@ -1,0 +1,84 @@
+"""Round-2 check of the sharded optimizer on real kernels (never run on GPUs yet - written after round 1's GPU minutes):
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 \
+        profiles/check_sharded.py [--graphed]
+
+Two trainers with identical weights on every rank, one replicated (all-reduce + full optimizer pass), one with
+shard_optimizer=True (reduce-scatter, slice-wise optimizer, operand all-gather under the forward); same per-rank batches
+and RNG seeds for a few steps; after gather_state() weights / EMA / moments must agree to atomics-ordering noise."""
+import argparse
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--graphed", action="store_true")
+    ap.add_argument("--steps", type=int, default=4)
+    args = ap.parse_args()
+    rank, local = int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    from oracle.fixtures import random_batch, random_state
+    from oracle.sit_oracle import ArchSpec
+    from reed_b200.image.loss import SILoss
+    from reed_b200.image.models.sit import SiT
+    from reed_b200.image.trainer import ReedTrainer
+
+    spec = ArchSpec(input_size=16, hidden_size=128, decoder_hidden_size=128, depth=3, num_heads=2, encoder_depth=1,
+                    z_dims=[64], projector_dim=128)
+
+    def build(shard):
+        m = SiT(path_type="linear", use_cfg=True, input_size=16, hidden_size=128, decoder_hidden_size=128, depth=3,
+                num_heads=2, encoder_depth=1, z_dims=[64], z_types=["i"], projector_dim=128, num_classes=1000,
+                fused_attn=True, qk_norm=False)
+        m.load_state_dict(random_state(spec, 11))
+        return ReedTrainer(m.to(dev).train(), SILoss(enc_names=["dinov2"], loss_weights={"dinov2": 1.0}),
+                           precision="bf16", shard_optimizer=shard)
+
+    batches = [random_batch(spec, 4, 100 + 10 * rank + i) for i in range(args.steps + 2)]
+    to_dev = lambda d: (d["x"].to(dev), d["y"].to(dev), [z.to(dev) for z in d["zs"]])
+    results = []
+    for shard in (False, True):
+        tr = build(shard)
+        torch.manual_seed(1000 + rank)
+        losses = []
+        if args.graphed:
+            tr.capture(*to_dev(batches[0]), warmup=2)
+            for i in range(args.steps):
+                losses.append(float(tr.train_step_graphed(*to_dev(batches[2 + i]))[0]))
+        else:
+            for i in (0, 0):
+                tr.train_step(*to_dev(batches[i]))
+            for i in range(args.steps):
+                losses.append(float(tr.train_step(*to_dev(batches[2 + i]))[0]))
+        tr.gather_state()
+        torch.cuda.synchronize()
+        named = {}
+        for b in tr.state.buckets:
+            for name, p, off in zip(b.names, b.params, b.offsets):
+                for field in ("param", "ema", "exp_avg", "shadow"):
+                    named[f"{name}/{field}"] = getattr(b, field)[off:off + p.numel()].float().clone()
+        results.append((losses, named, float(tr.grad_norm())))
+    (l0, n0, g0), (l1, n1, g1) = results
+    worst = max((float((n0[k] - n1[k]).abs().max()), k) for k in n0)
+    ok = all(abs(a - b) <= 1e-4 * max(1.0, abs(a)) for a, b in zip(l0, l1)) and worst[0] <= 5e-4 \
+        and abs(g0 - g1) <= 1e-3 * max(1.0, g0)
+    flag = torch.tensor([int(ok)], device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        print(f"losses replicated {l0}\nlosses sharded    {l1}\ngrad norm {g0} vs {g1}\nworst buffer diff {worst}")
+        print("SHARDED OPTIMIZER", "OK" if int(flag) else "MISMATCH")
+    dist.barrier()
+    dist.destroy_process_group()
+    sys.exit(0 if int(flag) else 1)
+
+
+if __name__ == "__main__":
+    main()

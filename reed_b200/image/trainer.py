@@ -36,6 +36,15 @@ class Bucket:
         self.offsets: List[int] = []
         self.numel = 0
         self.work = None
+        self.sharded = False       # optimizer state of this bucket is partitioned across the data-parallel ranks
+        self.gather_work = None    # in-flight all-gather of the bf16 shadows / fp32 masters (sharded optimizer)
+
+    def shard(self, rank: int, world: int):
+        """(first element, element count) of the slice rank ``rank`` owns; the whole bucket when it is not sharded."""
+        if not self.sharded:
+            return 0, self.numel
+        size = self.numel // world
+        return rank * size, size
 
     def add(self, name, p):
         self.names.append(name)
@@ -55,16 +64,22 @@ class _ZeroGroup:
 class FlatState:
     """Re-homes a model's parameters into flat per-bucket storage (works on any device; kernels need CUDA)."""
 
-    def __init__(self, model: nn.Module, ema: Optional[nn.Module] = None, with_shadow: bool = True):
+    def __init__(self, model: nn.Module, ema: Optional[nn.Module] = None, with_shadow: bool = True,
+                 shard_world: int = 1):
+        """shard_world > 1 lays the buckets out for the sharded optimizer (ReedTrainer(shard_optimizer=True)): block
+        buckets hold the 2-D weights only and are padded to ``shard_world`` equal 16-byte-aligned slices; every 1-D
+        parameter (biases are read in fp32 by the GEMM epilogues on every rank) moves to the replicated outer bucket."""
         self.model = model
+        self.shard_world = shard_world
         self.ema = ema
         self.buckets: List[Bucket] = []
         self.frozen: List[tuple] = []          # (param, ema_param) for requires_grad=False parameters
         ema_params = dict(ema.named_parameters()) if ema is not None else {}
         by_key: Dict[str, Bucket] = {}
 
-        def bucket_for(name):
-            key = ".".join(name.split(".")[:2]) if name.startswith("blocks.") else "outer"
+        def bucket_for(name, p):
+            in_block = name.startswith("blocks.") and not (shard_world > 1 and p.dim() == 1)
+            key = ".".join(name.split(".")[:2]) if in_block else "outer"
             if key not in by_key:
                 by_key[key] = Bucket(key)
                 self.buckets.append(by_key[key])
@@ -77,7 +92,14 @@ class FlatState:
             if not p.requires_grad:
                 self.frozen.append((p, ema_params.get(name)))
                 continue
-            bucket_for(name).add(name, p)
+            bucket_for(name, p).add(name, p)
+
+        if shard_world > 1:
+            quantum = _ALIGN * shard_world
+            for b in self.buckets:
+                if b.name != "outer":
+                    b.sharded = True
+                    b.numel = (b.numel + quantum - 1) // quantum * quantum     # the pad stays zero in every buffer
 
         for b in self.buckets:
             dev = b.params[0].device
@@ -158,7 +180,11 @@ class GradientReducer:
     def __init__(self, state: FlatState, group=None):
         self.state = state
         self.group = group
-        self.world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+        live = dist.is_available() and dist.is_initialized()
+        self.world = dist.get_world_size(group) if live else 1
+        self.rank = dist.get_rank(group) if live else 0
+        # gloo (the CPU tests) has neither reduce-scatter nor an in-place all-gather: fall back to all-reduce / a staged copy
+        self.nccl = live and dist.get_backend(group) == "nccl"
         self.enabled = True        # False while micro-batches of an accumulated step are still adding into the buckets
 
     @property
@@ -168,7 +194,22 @@ class GradientReducer:
     def launch(self, bucket: Bucket):
         if self.world == 1 or bucket.work is not None or not self.enabled:
             return
+        if bucket.sharded and self.nccl:
+            # sharded optimizer: every rank only needs the sum over ranks of its own slice (in place: NCCL's
+            # recvbuff == sendbuff + rank * recvcount form) - half the NVLink traffic of the all-reduce
+            lo, n = bucket.shard(self.rank, self.world)
+            bucket.work = dist.reduce_scatter_tensor(bucket.grad[lo:lo + n], bucket.grad, op=dist.ReduceOp.SUM,
+                                                     group=self.group, async_op=True)
+            return
         bucket.work = dist.all_reduce(bucket.grad, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+
+    def gather(self, bucket: Bucket, flat: torch.Tensor, async_op=False):
+        """All-gather a sharded bucket's flat buffer in place: every rank contributes the slice it owns."""
+        lo, n = bucket.shard(self.rank, self.world)
+        own = flat[lo:lo + n]
+        if not self.nccl:
+            own = own.clone()
+        return dist.all_gather_into_tensor(flat, own, group=self.group, async_op=async_op)
 
     def finish(self):
         for b in self.state.buckets:
@@ -184,7 +225,7 @@ class ReedTrainer:
 
     def __init__(self, model: nn.Module, loss_fn, *, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0,
                  max_grad_norm=1.0, ema_decay=0.9999, proj_coeff=0.5, precision: Optional[str] = "bf16", group=None,
-                 with_ema=True, comm_sms: int = 16):
+                 with_ema=True, comm_sms: int = 16, shard_optimizer: bool = False):
         self.model = model
         self.loss_fn = loss_fn
         self.lr, self.betas, self.eps, self.weight_decay = lr, betas, eps, weight_decay
@@ -197,7 +238,14 @@ class ReedTrainer:
             for p in self.ema.parameters():
                 p.requires_grad_(False)
             self.ema.eval()
-        self.state = FlatState(model, self.ema, with_shadow=True)
+        # Sharded optimizer (ZeRO-1 over NVSwitch; off by default): the clip/AdamW/EMA pass is HBM-bound at 38 B/param and
+        # every rank repeats it on identical data.  With shard_optimizer each rank reduce-scatters the block buckets,
+        # updates 1/world of every block's weights (masters, moments, EMA) and all-gathers only the bf16 GEMM operands
+        # - under the next forward, block by block.  Same arithmetic on every element; see _optimizer_step_sharded.
+        world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+        self.shard = bool(shard_optimizer) and world > 1
+        self.precision = precision
+        self.state = FlatState(model, self.ema, with_shadow=True, shard_world=world if self.shard else 1)
         self.reducer = GradientReducer(self.state, group)
         # SMs left to the NCCL kernels while backward overlaps the bucket all-reduces (bench.py caps NCCL's CTAs to match)
         self.comm_sms = comm_sms if self.reducer.world > 1 else 0
@@ -211,12 +259,17 @@ class ReedTrainer:
         self.step_count = 0
         dev = next(model.parameters()).device
         self._norm_sq = torch.zeros(1, device=dev, dtype=torch.float64)
+        self._norm_sq_shard = torch.zeros(1, device=dev, dtype=torch.float64)
+        self._operands_stale = False         # sharded optimizer: other ranks' slices of the GEMM operands are out of date
+        self._state_complete = True          # ... and of the masters / EMA / moments (gather_state() completes them)
         self._step_dev = torch.zeros(1, device=dev, dtype=torch.int32)   # device copy of step_count (graph replays)
         self._graph = None
         # all-reduce each block's bucket as soon as that block's backward has produced its last gradient
         for i, blk in enumerate(model.blocks):
             bucket = self.state.bucket_of_block(i)
             blk._reed_after_backward = (lambda b=bucket: self.reducer.launch(b))
+            if self.shard:                   # the block's operands arrive by all-gather: wait for this block's only
+                blk.register_forward_pre_hook(lambda _mod, _inp, b=bucket: self._await_operands(b))
 
     def compute_loss(self, images, labels, zs, diffusion_decay=1.0, repa_decay=1.0, time_input=None):
         """diffusion_decay / repa_decay: Python floats or 0-d device tensors (the curriculum scalars of train.py:363-385)."""
@@ -228,6 +281,8 @@ class ReedTrainer:
     def optimizer_step(self, device_step=False):
         """device_step: read the step from the device counter (incremented here by a kernel) instead of passing the
         host integer - the form a CUDA graph can replay."""
+        if self.shard:
+            return self._optimizer_step_sharded(device_step)
         self.step_count += 1
         self._step_dev += 1
         st = ops._stream()
@@ -246,6 +301,84 @@ class ReedTrainer:
         for p, ep in self.state.frozen:
             if ep is not None:
                 ops._launch("reed_ema_update", p.data_ptr(), ep.data_ptr(), p.numel(), self.ema_decay, st)
+
+    # -- sharded optimizer ---------------------------------------------------------------------------------------
+    def _k_sumsq(self, flat, out):
+        ops._launch("reed_grad_sumsq", flat.data_ptr(), flat.numel(), out.data_ptr(), ops._stream())
+
+    def _k_adamw(self, b: Bucket, lo: int, n: int, device_step: bool):
+        """clip + AdamW + EMA + shadow refresh on elements [lo, lo+n) of bucket b (lo is a multiple of 8 elements)."""
+        clip = self.max_grad_norm is not None and self.max_grad_norm > 0
+        ema = b.ema if b.ema is not None else b.param
+        ops._launch("reed_adamw_ema", b.param[lo:].data_ptr(), b.grad[lo:].data_ptr(), b.exp_avg[lo:].data_ptr(),
+                    b.exp_avg_sq[lo:].data_ptr(), ema[lo:].data_ptr(),
+                    b.shadow[lo:].data_ptr() if b.shadow is not None else None, n,
+                    self._norm_sq.data_ptr() if clip else None, float(self.max_grad_norm or 0.0),
+                    self.reducer.grad_scale, self.lr, self.betas[0], self.betas[1], self.eps, self.weight_decay,
+                    0 if device_step else self.step_count, self.ema_decay if b.ema is not None else 0.0,
+                    self._step_dev.data_ptr() if device_step else None, ops._stream())
+
+    def _optimizer_step_sharded(self, device_step=False):
+        """After the reduce-scatters each rank holds the summed gradient of its slice of every block bucket (and, after
+        the all-reduce, of the whole outer bucket).  Global norm = all-reduce of the slices' sums of squares + the outer
+        bucket's; then the fused kernel runs on the owned slices only: 38 B/param over 1/world of the weights."""
+        self.step_count += 1
+        self._step_dev += 1
+        r, w = self.reducer.rank, self.reducer.world
+        self._norm_sq.zero_()
+        self._norm_sq_shard.zero_()
+        for b in self.state.buckets:
+            lo, n = b.shard(r, w)
+            self._k_sumsq(b.grad[lo:lo + n], self._norm_sq_shard if b.sharded else self._norm_sq)
+        dist.all_reduce(self._norm_sq_shard, op=dist.ReduceOp.SUM, group=self.reducer.group)
+        self._norm_sq += self._norm_sq_shard
+        for b in self.state.buckets:
+            lo, n = b.shard(r, w)
+            self._k_adamw(b, lo, n, device_step)
+        for p, ep in self.state.frozen:
+            if ep is not None:
+                ops._launch("reed_ema_update", p.data_ptr(), ep.data_ptr(), p.numel(), self.ema_decay, ops._stream())
+        self._operands_stale = True
+        self._state_complete = False
+
+    def _operand_buffers(self, b: Bucket):
+        """What the forward reads of a block bucket: bf16 shadows in bf16 mode, fp32 masters in fp32 mode (both when the
+        mode follows torch.autocast)."""
+        if self.precision == "bf16":
+            return [b.shadow]
+        if self.precision == "fp32":
+            return [b.param]
+        return [b.shadow, b.param]
+
+    def _gather_operands(self, force=False):
+        """Start the all-gathers that bring every rank's updated slices of the GEMM operands to this rank, in forward
+        order on NCCL's stream; block i's forward waits for bucket i only (_await_operands)."""
+        if not self.shard or not (self._operands_stale or force):
+            return
+        for b in self.state.buckets:
+            if b.sharded:
+                b.gather_work = [self.reducer.gather(b, flat, async_op=True) for flat in self._operand_buffers(b)]
+        self._operands_stale = False
+
+    def _await_operands(self, b: Bucket):
+        if b.gather_work is not None:
+            for work in b.gather_work:
+                work.wait()
+            b.gather_work = None
+
+    def gather_state(self):
+        """Make every rank's copy of the sharded buffers complete (masters, EMA, moments, shadows): call before reading
+        ``model`` / ``ema`` weights outside the train step (sampling, evaluation, checkpoints).  No-op when not sharded."""
+        if not self.shard:
+            return
+        for b in self.state.buckets:
+            self._await_operands(b)
+            if b.sharded:
+                for flat in (b.param, b.exp_avg, b.exp_avg_sq, b.ema, b.shadow):
+                    if flat is not None:
+                        self.reducer.gather(b, flat)
+        self._operands_stale = False
+        self._state_complete = True
 
     def _backward(self, loss):
         """backward with the per-bucket all-reduces in flight; the GEMM grids shrink by comm_sms SMs meanwhile."""
@@ -277,6 +410,11 @@ class ReedTrainer:
     def checkpoint(self, args=None, steps: Optional[int] = None) -> dict:
         """Snapshot as the dict the reference passes to ``torch.save`` (train.py:420-426).  Tensors are copies: the
         live parameters are views of the flat buckets, and ``torch.save`` of a view would write the whole bucket."""
+        if self.shard and not self._state_complete:
+            # gather_state() is a collective; the reference saves on the main process only (train.py:419), so it cannot
+            # be hidden in here
+            raise RuntimeError("sharded optimizer: call trainer.gather_state() on EVERY rank before checkpoint()")
+
         def copied(sd):
             return type(sd)((k, v.detach().clone()) for k, v in sd.items())
         groups = torch.optim.AdamW(self.model.parameters(), lr=self.lr, betas=tuple(self.betas), eps=self.eps,
@@ -332,6 +470,7 @@ class ReedTrainer:
         return int(ckpt.get("steps", step))
 
     def train_step(self, images, labels, zs, diffusion_decay=1.0, repa_decay=1.0):
+        self._gather_operands()
         self.state.begin_step()
         loss, out = self.compute_loss(images, labels, zs, diffusion_decay, repa_decay)
         self._backward(loss)
@@ -348,6 +487,7 @@ class ReedTrainer:
         k = len(micro_batches)
         if k == 0:
             raise ValueError("train_step_accumulated needs at least one micro-batch")
+        self._gather_operands()
         self.state.begin_step()
         total, outs = 0.0, []
         for i, (images, labels, zs) in enumerate(micro_batches):
@@ -372,6 +512,7 @@ class ReedTrainer:
     # call and copied into the graph's static input; device randomness (noise, label dropout) is captured through
     # torch's graph-safe generator state.
     def _step_body(self, g):
+        self._gather_operands(force=True)      # recorded in the graph: every replay starts by completing the operands
         self.state.begin_step()
         loss, out = self.compute_loss(g["images"], g["labels"], g["zs"], g["scalars"][0], g["scalars"][1],
                                       time_input=g["time"])
@@ -420,5 +561,6 @@ class ReedTrainer:
         for dst, src in zip(g["zs"], zs):
             dst.copy_(src, non_blocking=True)
         self._graph.replay()
+        self._state_complete = not self.shard
         self.step_count += 1
         return g["loss"], g["out"]
