@@ -140,3 +140,25 @@ def test_gemm_reserve_sms_is_host_state():
     _cabi.call("reed_gemm_reserve_sms", 0)
     with pytest.raises(_cabi.ReedLibraryError):
         _cabi.call("reed_gemm_reserve_sms", 1000)
+
+
+def test_argument_errors_are_reported_without_a_device(built):
+    """Argument validation happens before any CUDA call: non-zero return + reed_last_error(), no launch, no device needed."""
+    lib = built.load()
+    cases = [
+        ("reed_sample_posterior", (None, None, None, None, 1.0, 0.0, None, -1, 4, 16, None), "sample_posterior: bad shape"),
+        ("reed_sampler_step", (None, None, 0, None, None, None, None, None, 8, 0, 0, 1, 7, 1.0, 0.5, -0.1, None),
+         "path_type"),
+        ("reed_gemm_reserve_sms", (65,), "out of range"),
+        ("reed_unary", (None, 0, None, 1, 0, 6, None), "n % 4"),
+        ("reed_adamw_ema", (None, None, None, None, None, None, 8, None, 1.0, 1.0, 1e-4, 0.9, 0.999, 1e-8, 0.0, 0, 0.9999,
+                            None, None), "1-based"),
+    ]
+    for name, args, needle in cases:
+        with pytest.raises(built.ReedLibraryError, match=name) as err:
+            built.call(name, *args)
+        assert needle in str(err.value), (name, str(err.value))
+    assert getattr(lib, "reed_gemm_reserve_sms")(0) == 0          # and a valid host-only call succeeds
+    # zero-sized work returns before touching the device as well
+    built.call("reed_sample_posterior", None, None, None, None, 1.0, 0.0, None, 0, 4, 16, None)
+    built.call("reed_grad_sumsq", None, 0, None, None)
