@@ -168,7 +168,8 @@ def build_trainer(cfg, dev, precision="bf16"):
     # REED_SHARD_OPT=1: sharded optimizer (reduce-scatter + slice-wise clip/AdamW/EMA + operand all-gather); off by default
     # until it has been validated on GPUs (profiles/check_sharded.py)
     return ReedTrainer(model, loss_fn, precision=precision, comm_sms=int(os.environ.get("REED_COMM_SMS", "16")),
-                       shard_optimizer=os.environ.get("REED_SHARD_OPT", "0") == "1"), spec
+                       shard_optimizer=os.environ.get("REED_SHARD_OPT", "0") == "1" or os.environ.get("REED_NVLS", "0") == "1",
+                       nvls=os.environ.get("REED_NVLS", "0") == "1"), spec
 
 
 def make_batches(cfg, spec, dev, n_buf):
@@ -375,7 +376,8 @@ def run_gpu_arm(args, cfg):
             "steps": args.steps, "warmup": n_warm, "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": cfg["workload"], "model": cfg["model"], "local_batch": B, "global_batch": B * world,
-                       "tokens": T, "parallelism": f"dp{world}", "optimizer": "sharded over ranks" if trainer.shard else "replicated", "l2": "per-step working set (activations, weights) far exceeds the 126 MB L2; "
+                       "tokens": T, "parallelism": f"dp{world}", "optimizer": ("sharded over ranks, NVLS multicast exchange" if trainer.nvls is not None else "sharded over ranks, NCCL")
+                       if trainer.shard else "replicated", "l2": "per-step working set (activations, weights) far exceeds the 126 MB L2; "
                        f"{n_buf} rotating input batches", "precision": "bf16 GEMM operands, fp32 accumulate/residual/master weights",
                        "launch": "CUDA graph replay of the whole step" if graphed else "eager (one launch per kernel from Python)"},
             "model_flops_per_image": train_flops,

@@ -139,6 +139,19 @@ int reed_sampler_step(const void* x_cur, const void* v, int model_dtype, const v
                       int path_type, double cfg, double t_cur, double dt, void* stream);
 int reed_sampler_cast(const void* x, void* x_model, int model_dtype, int64_t n, int dup, void* stream);
 
+/* Gradient exchange of the data-parallel step over NVSwitch multicast (NVLS), fused with the arithmetic on either side
+ * (train.py:151,293,401 DDP all-reduce -> 402-412 clip / AdamW / EMA).  Buffers are symmetric-memory allocations with a
+ * multicast mapping; the caller orders ranks with stream barriers (see reed_b200/image/nvls.py).
+ *   reduce_scatter_sumsq: grad_local[lo, lo+n) = SUM over ranks of that slice, read through grad_multicast with
+ *     multimem.ld_reduce (the switch adds in flight); *norm_sq (double, optional) += sum of squares of the result.
+ *   adamw_ema_mc: reed_adamw_ema on an owned slice whose bf16 operands are stored through the multicast address
+ *     (shadow_multicast, already offset to the slice): the all-gather of the new weights rides in the optimizer's stores. */
+int reed_nvls_reduce_scatter_sumsq(const void* grad_multicast, void* grad_local, int64_t lo, int64_t n, void* norm_sq,
+                                   int ctas, void* stream);
+int reed_adamw_ema_mc(void* p, const void* g, void* m, void* v, void* ema, void* shadow_multicast, int64_t n,
+                      const void* norm_sq, float max_norm, float grad_scale, float lr, float beta1, float beta2, float eps,
+                      float weight_decay, int step, float ema_decay, const void* step_dev, void* stream);
+
 /* VAE-posterior draw of the latent data path (train.py:84-91 sample_posterior with the per-channel latents_scale /
  * latents_bias of train.py:226-231): out[b,c,:] = ((moments[b,c,:] + moments[b,C+c,:] * noise[b,c,:]) * scale[c]) + bias[c],
  * every operation rounded separately (bit-identical to the reference's PyTorch kernel sequence for the same noise).

@@ -1,7 +1,7 @@
 """Round-2 check of the sharded optimizer on real kernels (never run on GPUs yet - written after round 1's GPU minutes):
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 \
-        profiles/check_sharded.py [--graphed]
+        profiles/check_sharded.py [--graphed] [--nvls]
 
 Two trainers with identical weights on every rank, one replicated (all-reduce + full optimizer pass), one with
 shard_optimizer=True (reduce-scatter, slice-wise optimizer, operand all-gather under the forward); same per-rank batches
@@ -19,6 +19,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--graphed", action="store_true")
+    ap.add_argument("--nvls", action="store_true", help="multicast reduce-scatter / operand stores (csrc/nvls.cu) instead of NCCL")
     ap.add_argument("--steps", type=int, default=4)
     args = ap.parse_args()
     rank, local = int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"])
@@ -40,7 +41,7 @@ def main():
                 fused_attn=True, qk_norm=False)
         m.load_state_dict(random_state(spec, 11))
         return ReedTrainer(m.to(dev).train(), SILoss(enc_names=["dinov2"], loss_weights={"dinov2": 1.0}),
-                           precision="bf16", shard_optimizer=shard)
+                           precision="bf16", shard_optimizer=shard, nvls=shard and args.nvls)
 
     batches = [random_batch(spec, 4, 100 + 10 * rank + i) for i in range(args.steps + 2)]
     to_dev = lambda d: (d["x"].to(dev), d["y"].to(dev), [z.to(dev) for z in d["zs"]])

@@ -45,6 +45,8 @@ _SIGNATURES = {
     "reed_grad_sumsq": [P, L, P, P],
     "reed_adamw_ema": [P, P, P, P, P, P, L, P, F, F, F, F, F, F, F, I, F, P, P],
     "reed_ema_update": [P, P, L, F, P],
+    "reed_nvls_reduce_scatter_sumsq": [P, P, L, L, P, I, P],
+    "reed_adamw_ema_mc": [P, P, P, P, P, P, L, P, F, F, F, F, F, F, F, I, F, P, P],
 }
 
 EXPORTS = sorted(list(_SIGNATURES) + ["reed_version", "reed_last_error"])

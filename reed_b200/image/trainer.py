@@ -67,12 +67,17 @@ class FlatState:
     """Re-homes a model's parameters into flat per-bucket storage (works on any device; kernels need CUDA)."""
 
     def __init__(self, model: nn.Module, ema: Optional[nn.Module] = None, with_shadow: bool = True,
-                 shard_world: int = 1):
+                 shard_world: int = 1, alloc=None):
         """shard_world > 1 lays the buckets out for the sharded optimizer (ReedTrainer(shard_optimizer=True)): block
         buckets hold the 2-D weights only and are padded to ``shard_world`` equal 16-byte-aligned slices; every 1-D
         parameter (biases are read in fp32 by the GEMM epilogues on every rank) moves to the replicated outer bucket."""
         self.model = model
         self.shard_world = shard_world
+
+        def new(kind, b, dtype):
+            """``alloc(kind, bucket, numel, dtype, device)`` may supply a buffer (nvls.py: symmetric memory); else zeros."""
+            t = alloc(kind, b, b.numel, dtype, b.params[0].device) if alloc is not None else None
+            return t if t is not None else torch.zeros(b.numel, device=b.params[0].device, dtype=dtype)
         self.ema = ema
         self.buckets: List[Bucket] = []
         self.frozen: List[tuple] = []          # (param, ema_param) for requires_grad=False parameters
@@ -106,11 +111,11 @@ class FlatState:
         for b in self.buckets:
             dev = b.params[0].device
             b.param = torch.zeros(b.numel, device=dev, dtype=torch.float32)
-            b.grad = torch.zeros(b.numel, device=dev, dtype=torch.float32)
+            b.grad = new("grad", b, torch.float32)
             b.exp_avg = torch.zeros(b.numel, device=dev, dtype=torch.float32)
             b.exp_avg_sq = torch.zeros(b.numel, device=dev, dtype=torch.float32)
             b.ema = torch.zeros(b.numel, device=dev, dtype=torch.float32) if ema is not None else None
-            b.shadow = torch.zeros(b.numel, device=dev, dtype=torch.bfloat16) if with_shadow else None
+            b.shadow = new("shadow", b, torch.bfloat16) if with_shadow else None
             for name, p, off in zip(b.names, b.params, b.offsets):
                 n = p.numel()
                 view = b.param[off:off + n].view(p.shape)
@@ -189,6 +194,8 @@ class GradientReducer:
         # gloo (the CPU tests) has neither reduce-scatter nor an in-place all-gather: fall back to all-reduce / a staged copy
         self.nccl = live and dist.get_backend(group) == "nccl"
         self.enabled = True        # False while micro-batches of an accumulated step are still adding into the buckets
+        self.nvls = None           # nvls.NvlsExchange: multicast reduce-scatter kernels instead of NCCL for sharded buckets
+        self.norm_sq_shard = None  # ... which also accumulate the owned slices' sums of squares into this device scalar
 
     @property
     def grad_scale(self):
@@ -196,6 +203,9 @@ class GradientReducer:
 
     def launch(self, bucket: Bucket):
         if self.world == 1 or bucket.work is not None or not self.enabled:
+            return
+        if bucket.sharded and self.nvls is not None:
+            bucket.work = self.nvls.reduce_scatter(bucket, self.rank, self.world, self.norm_sq_shard)
             return
         if bucket.sharded and self.nccl:
             # sharded optimizer: every rank only needs the sum over ranks of its own slice (in place: NCCL's
@@ -228,7 +238,7 @@ class ReedTrainer:
 
     def __init__(self, model: nn.Module, loss_fn, *, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0,
                  max_grad_norm=1.0, ema_decay=0.9999, proj_coeff=0.5, precision: Optional[str] = "bf16", group=None,
-                 with_ema=True, comm_sms: int = 16, shard_optimizer: bool = False):
+                 with_ema=True, comm_sms: int = 16, shard_optimizer: bool = False, nvls: bool = False):
         self.model = model
         self.loss_fn = loss_fn
         self.lr, self.betas, self.eps, self.weight_decay = lr, betas, eps, weight_decay
@@ -248,7 +258,14 @@ class ReedTrainer:
         world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
         self.shard = bool(shard_optimizer) and world > 1
         self.precision = precision
-        self.state = FlatState(model, self.ema, with_shadow=True, shard_world=world if self.shard else 1)
+        # nvls (needs shard_optimizer, bf16 operands, NCCL group on one NVSwitch domain): the reduce-scatter and the
+        # operand all-gather become multicast loads / stores inside our own kernels (csrc/nvls.cu, image/nvls.py)
+        self.nvls = None
+        if self.shard and nvls and precision == "bf16" and dist.get_backend(group) == "nccl":
+            from .nvls import NvlsExchange
+            self.nvls = NvlsExchange(group, ctas=comm_sms or 16)
+        self.state = FlatState(model, self.ema, with_shadow=True, shard_world=world if self.shard else 1,
+                               alloc=self.nvls.alloc if self.nvls is not None else None)
         self.reducer = GradientReducer(self.state, group)
         # SMs left to the NCCL kernels while backward overlaps the bucket all-reduces (bench.py caps NCCL's CTAs to match)
         self.comm_sms = comm_sms if self.reducer.world > 1 else 0
@@ -263,6 +280,9 @@ class ReedTrainer:
         dev = next(model.parameters()).device
         self._norm_sq = torch.zeros(1, device=dev, dtype=torch.float64)
         self._norm_sq_shard = torch.zeros(1, device=dev, dtype=torch.float64)
+        if self.nvls is not None:
+            self.nvls.attach(self.state)
+            self.reducer.nvls, self.reducer.norm_sq_shard = self.nvls, self._norm_sq_shard
         self._operands_stale = False         # sharded optimizer: other ranks' slices of the GEMM operands are out of date
         self._state_complete = True          # ... and of the masters / EMA / moments (gather_state() completes them)
         self._step_dev = torch.zeros(1, device=dev, dtype=torch.int32)   # device copy of step_count (graph replays)
@@ -282,6 +302,8 @@ class ReedTrainer:
         self.state.begin_step()
         if self._early_norm:
             self._norm_sq.zero_()
+        if self.nvls is not None:            # the multicast reduce-scatter kernels add their slices' squares during backward
+            self._norm_sq_shard.zero_()
 
     def _after_block_backward(self, bucket: Bucket):
         self.reducer.launch(bucket)
@@ -330,6 +352,14 @@ class ReedTrainer:
         """clip + AdamW + EMA + shadow refresh on elements [lo, lo+n) of bucket b (lo is a multiple of 8 elements)."""
         clip = self.max_grad_norm is not None and self.max_grad_norm > 0
         ema = b.ema if b.ema is not None else b.param
+        if b.sharded and self.nvls is not None:     # bf16 operands stored through the multicast address: no all-gather
+            ops._launch("reed_adamw_ema_mc", b.param[lo:].data_ptr(), b.grad[lo:].data_ptr(), b.exp_avg[lo:].data_ptr(),
+                        b.exp_avg_sq[lo:].data_ptr(), ema[lo:].data_ptr(), b.shadow_mc + 2 * lo, n,
+                        self._norm_sq.data_ptr() if clip else None, float(self.max_grad_norm or 0.0),
+                        self.reducer.grad_scale, self.lr, self.betas[0], self.betas[1], self.eps, self.weight_decay,
+                        0 if device_step else self.step_count, self.ema_decay if b.ema is not None else 0.0,
+                        self._step_dev.data_ptr() if device_step else None, ops._stream())
+            return
         ops._launch("reed_adamw_ema", b.param[lo:].data_ptr(), b.grad[lo:].data_ptr(), b.exp_avg[lo:].data_ptr(),
                     b.exp_avg_sq[lo:].data_ptr(), ema[lo:].data_ptr(),
                     b.shadow[lo:].data_ptr() if b.shadow is not None else None, n,
@@ -346,10 +376,12 @@ class ReedTrainer:
         self._step_dev += 1
         r, w = self.reducer.rank, self.reducer.world
         self._norm_sq.zero_()
-        self._norm_sq_shard.zero_()
+        if self.nvls is None:
+            self._norm_sq_shard.zero_()
         for b in self.state.buckets:
             lo, n = b.shard(r, w)
-            self._k_sumsq(b.grad[lo:lo + n], self._norm_sq_shard if b.sharded else self._norm_sq)
+            if not (b.sharded and self.nvls is not None):        # else: summed by reed_nvls_reduce_scatter_sumsq already
+                self._k_sumsq(b.grad[lo:lo + n], self._norm_sq_shard if b.sharded else self._norm_sq)
         dist.all_reduce(self._norm_sq_shard, op=dist.ReduceOp.SUM, group=self.reducer.group)
         self._norm_sq += self._norm_sq_shard
         for b in self.state.buckets:
@@ -374,6 +406,10 @@ class ReedTrainer:
         """Start the all-gathers that bring every rank's updated slices of the GEMM operands to this rank, in forward
         order on NCCL's stream; block i's forward waits for bucket i only (_await_operands)."""
         if not self.shard or not (self._operands_stale or force):
+            return
+        if self.nvls is not None:              # operands arrived by multicast stores: one barrier opens the step
+            self.nvls.open_step(self.state)
+            self._operands_stale = False
             return
         for b in self.state.buckets:
             if b.sharded:
