@@ -80,6 +80,30 @@ def _by_name(tr, field):
     return out
 
 
+class _FakeMulticast:
+    """Stands in for nvls.NvlsExchange on CPU: same calls, torch collectives instead of multimem loads / stores."""
+
+    class _Done:
+        def wait(self):
+            pass
+
+    def __init__(self, trainer):
+        self.tr = trainer
+        self.opened = 0
+
+    def reduce_scatter(self, bucket, rank, world, norm_sq):
+        dist.all_reduce(bucket.grad)                                  # ld_reduce: the owned slice arrives summed ...
+        lo, n = bucket.shard(rank, world)
+        norm_sq += bucket.grad[lo:lo + n].double().pow(2).sum()       # ... and its squares are added in the same pass
+        return self._Done()
+
+    def open_step(self, state):                                       # multimem.st: every rank's slice lands everywhere
+        self.opened += 1
+        for b in state.buckets:
+            if b.sharded:
+                self.tr.reducer.gather(b, b.shadow)
+
+
 def _worker(rank, world, port, out):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -135,6 +159,33 @@ def _worker(rank, world, port, out):
             for field in ("param", "ema", "exp_avg", "exp_avg_sq"):
                 want, got = _by_name(rep, field), _by_name(shd, field)
                 ok &= all(torch.equal(want[k], got[k]) for k in want)
+        # the multicast-exchange wiring (norm partials from the reduce-scatter, one barrier instead of all-gathers)
+        rep2 = ReedTrainer(_tiny_model(), None, precision="bf16")
+        mc = ReedTrainer(_tiny_model(), None, precision="bf16", shard_optimizer=True)
+        for tr in (rep2, mc):
+            _emulate_kernels(tr)
+        mc.nvls = _FakeMulticast(mc)
+        mc.reducer.nvls, mc.reducer.norm_sq_shard = mc.nvls, mc._norm_sq_shard
+        for step in (1, 2):
+            mc._gather_operands()
+            mc._begin_step()
+            for tr in (rep2, mc):
+                _fill_grads(tr, rank, step)
+            rep2.reducer.finish()
+            _replicated_step(rep2)
+            mc.reducer.launch(mc.state.bucket_of_block(1))
+            mc.reducer.finish()
+            mc.optimizer_step()
+            ok &= abs(float(mc._norm_sq) - float(rep2._norm_sq)) <= 1e-9 * float(rep2._norm_sq)
+        ok &= mc.nvls.opened == 1 and mc._operands_stale
+        mc._gather_operands()
+        ok &= mc.nvls.opened == 2 and all(b.gather_work is None for b in mc.state.buckets)
+        want, got = _by_name(rep2, "shadow"), _by_name(mc, "shadow")
+        ok &= all(torch.equal(want[k], got[k]) for k in want)
+        mc.gather_state()
+        for field in ("param", "ema", "exp_avg_sq"):
+            want, got = _by_name(rep2, field), _by_name(mc, field)
+            ok &= all(torch.equal(want[k], got[k]) for k in want)
         ck = shd.checkpoint()
         ok &= ck["steps"] == 3 and all(torch.equal(v, rep.model.state_dict()[k]) for k, v in ck["model"].items())
         out[rank] = bool(ok)
