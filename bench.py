@@ -59,8 +59,10 @@ def spec_for(cfg):
 # CPU arm: the oracle port of the reference step (also the cpu_baseline leg of the GPU arm)
 # ---------------------------------------------------------------------------------------------------------
 
-def cpu_reference_steps(cfg, steps, warmup, batch=None):
-    """Times clip+AdamW+EMA train steps of the oracle (torch CPU, fp32, all host threads). Returns (img/s, info)."""
+def cpu_reference_steps(cfg, steps, warmup, batch=None, budget_s=None):
+    """Times clip+AdamW+EMA train steps of the oracle (torch CPU, fp32, all host threads). Returns (img/s, s/step, info).
+    budget_s bounds the sample: no new step is started once the wall clock since the first timed step exceeds it (at least one
+    timed step always runs); info["steps"] is the number actually timed."""
     from oracle import loss_oracle, sit_oracle, train_oracle
     from oracle.fixtures import random_batch, random_state
     torch.set_num_threads(os.cpu_count() or 1)
@@ -72,7 +74,12 @@ def cpu_reference_steps(cfg, steps, warmup, batch=None):
     m1 = {k: torch.zeros_like(v) for k, v in sd.items()}
     m2 = {k: torch.zeros_like(v) for k, v in sd.items()}
     times = []
+    started = None
     for it in range(warmup + steps):
+        if it >= warmup:
+            started = started if started is not None else time.perf_counter()
+            if budget_s is not None and times and time.perf_counter() - started > budget_s:
+                break
         data = random_batch(spec, batch, 100 + it)
         t0 = time.perf_counter()
         leaves = {k: p.detach().requires_grad_(k != "pos_embed") for k, p in params.items()}
@@ -87,8 +94,8 @@ def cpu_reference_steps(cfg, steps, warmup, batch=None):
         if it >= warmup:
             times.append(dt)
     per_step = sum(times) / len(times)
-    info = dict(kind="port", cores=torch.get_num_threads(),
-                sample=f"{steps} timed step(s) of the CPU oracle port (reference algorithm, torch fp32), batch {batch}, "
+    info = dict(kind="port", cores=torch.get_num_threads(), steps=len(times),
+                sample=f"{len(times)} timed step(s) of the CPU oracle port (reference algorithm, torch fp32), batch {batch}, "
                        f"after {warmup} warm-up")
     return batch / per_step, per_step, info
 
@@ -97,8 +104,11 @@ def run_reference_arm(args, cfg):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps, warmup = max(1, min(args.steps, 3)), max(1, min(args.warmup, 1))
-    ips, per_step, info = cpu_reference_steps(cfg, steps, warmup)
+    # the driver passes the GPU arm's --steps/--warmup: honour them up to a wall-clock budget (a CPU step of SiT-XL/2 at
+    # batch 4 takes seconds), and report the number of steps actually timed
+    warmup = max(1, min(args.warmup, 2))
+    ips, per_step, info = cpu_reference_steps(cfg, max(1, min(args.steps, 20)), warmup, budget_s=90.0)
+    steps = info["steps"]
     info["value"] = ips
     info["unit"] = "images/s"
     line = {
@@ -369,8 +379,9 @@ def run_gpu_arm(args, cfg):
             peaks_burst = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops"]
         except Exception:
             pass
-        steps_cpu, warm_cpu = 2, 1
-        cpu_ips, _, cpu_info = cpu_reference_steps(cfg, steps_cpu, warm_cpu) if world == 1 and not args.skip_cpu else (None, None, None)
+        steps_cpu, warm_cpu = 8, 1          # bounded sample: stops after ~15 s of timed CPU work
+        cpu_ips, _, cpu_info = (cpu_reference_steps(cfg, steps_cpu, warm_cpu, budget_s=15.0)
+                                if world == 1 and not args.skip_cpu else (None, None, None))
         line = {
             "metric": "SiT REED train images/sec", "value": value, "unit": "images/s", "n_gpus": world,
             "steps": args.steps, "warmup": n_warm, "ms_per_step": ms / args.steps,
