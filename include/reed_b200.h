@@ -152,6 +152,13 @@ int reed_adamw_ema_mc(void* p, const void* g, void* m, void* v, void* ema, void*
                       const void* norm_sq, float max_norm, float grad_scale, float lr, float beta1, float beta2, float eps,
                       float weight_decay, int step, float ema_decay, const void* step_dev, void* stream);
 
+/* Raw-image preprocessing for the frozen target encoders (train.py:53-74 preprocess_raw_image): x/255, per-channel
+ * (x - mean)/std, bicubic resize (ATen upsample_bicubic2d, align_corners=False, A=-0.75) to out_size when out_size != in_size.
+ *   src [batch, channels, in_size, in_size] uint8 (src_dtype 2) or fp32 (0), values 0..255; dst fp32 (0) or bf16 (1);
+ *   mean / stdv: HOST arrays of `channels` (<= 4) floats; resize_first = 1 for the clip order (resize, then normalise). */
+int reed_preprocess_image(const void* src, int src_dtype, void* dst, int dst_dtype, int batch, int channels, int in_size,
+                          int out_size, const float* mean, const float* stdv, int resize_first, void* stream);
+
 /* VAE-posterior draw of the latent data path (train.py:84-91 sample_posterior with the per-channel latents_scale /
  * latents_bias of train.py:226-231): out[b,c,:] = ((moments[b,c,:] + moments[b,C+c,:] * noise[b,c,:]) * scale[c]) + bias[c],
  * every operation rounded separately (bit-identical to the reference's PyTorch kernel sequence for the same noise).

@@ -207,8 +207,35 @@ def curriculum_case():
     return cases
 
 
+def preprocess_case():
+    """train.py:53-74 executed from the reference source on a seeded uint8 batch; a strided sample of every output plus
+    whole-tensor checksums (the full 3x224x224 outputs would be megabytes)."""
+    from torchvision.transforms import Normalize
+    src = open(os.path.join(REF, "train.py")).read()
+    ns = {"torch": torch, "Normalize": Normalize,
+          "IMAGENET_DEFAULT_MEAN": (0.485, 0.456, 0.406), "IMAGENET_DEFAULT_STD": (0.229, 0.224, 0.225)}   # timm.data constants
+    for node in ast.parse(src).body:
+        if isinstance(node, ast.Assign) and getattr(node.targets[0], "id", "") in ("CLIP_DEFAULT_MEAN", "CLIP_DEFAULT_STD"):
+            exec(compile(ast.Module([node], []), "train.py", "exec"), ns)
+        if isinstance(node, ast.FunctionDef) and node.name == "preprocess_raw_image":
+            exec(compile(ast.Module([node], []), "train.py", "exec"), ns)
+    cases = {}
+    for enc_type, res, seed in (("dinov2", 256, 1), ("dinov2", 512, 2), ("clip", 256, 3), ("mocov3", 256, 4),
+                                ("jepa", 256, 5), ("dinov1", 256, 6), ("mae", 256, 7), ("siglip", 256, 8)):
+        x = torch.randint(0, 256, (2, 3, res, res), generator=torch.Generator().manual_seed(seed), dtype=torch.uint8)
+        y = ns["preprocess_raw_image"](x, enc_type)
+        cases[f"{enc_type}/{res}"] = dict(enc_type=enc_type, resolution=res, seed=seed, shape=tuple(y.shape), dtype=str(y.dtype),
+                                          sample=y[..., ::7, ::5].clone(), total=float(y.double().sum()),
+                                          abs_total=float(y.double().abs().sum()))
+    return cases
+
+
 def main():
     from .sit_oracle import ArchSpec
+    if "--only-preprocess" in sys.argv:
+        torch.save(preprocess_case(), os.path.join(OUT, "preprocess.pt"))
+        print("preprocess.pt", os.path.getsize(os.path.join(OUT, "preprocess.pt")))
+        return
     if "--only-curriculum" in sys.argv:
         _import_reference()
         torch.save(curriculum_case(), os.path.join(OUT, "curriculum.pt"))
@@ -245,6 +272,7 @@ def main():
     torch.save(init_b, os.path.join(OUT, "init_b2.pt"))
     torch.save(train_glue_case(ref_sit, ref_loss, ns, spec_t, state_seed=21), os.path.join(OUT, "train_glue.pt"))
     torch.save(curriculum_case(), os.path.join(OUT, "curriculum.pt"))
+    torch.save(preprocess_case(), os.path.join(OUT, "preprocess.pt"))
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

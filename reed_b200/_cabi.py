@@ -41,6 +41,7 @@ _SIGNATURES = {
     "reed_siloss_cos_bwd": [P, I, P, I, P, P, P, I, I, I, P],
     "reed_sampler_step": [P, P, I, P, P, P, P, P, L, I, I, I, I, D, D, D, P],
     "reed_sampler_cast": [P, P, I, L, I, P],
+    "reed_preprocess_image": [P, I, P, I, I, I, I, I, P, P, I, P],
     "reed_sample_posterior": [P, P, P, P, F, F, P, I, I, I, P],
     "reed_grad_sumsq": [P, L, P, P],
     "reed_adamw_ema": [P, P, P, P, P, P, L, P, F, F, F, F, F, F, F, I, F, P, P],

@@ -70,3 +70,30 @@ def test_single_micro_batch_accumulated_step_equals_plain_step():
         assert float((ba.param - bb.param).abs().max()) <= 2e-5
         assert float((ba.ema - bb.ema).abs().max()) <= 2e-5
     assert a.step_count == b.step_count == 1
+
+
+def test_preprocess_raw_image_matches_reference_golden(golden):
+    """train.py:53-74 on the GPU kernel: against outputs of the reference function, the tap-level oracle and torch's own ops."""
+    import torch.nn.functional as F
+    from oracle import preprocess_oracle
+    from reed_b200.image.preprocess import preprocess_raw_image
+    for name, case in golden("preprocess.pt").items():
+        r = case["resolution"]
+        x = torch.randint(0, 256, (2, 3, r, r), generator=torch.Generator().manual_seed(case["seed"]), dtype=torch.uint8)
+        y = preprocess_raw_image(x.to(DEV), case["enc_type"])
+        assert tuple(y.shape) == case["shape"] and str(y.dtype) == case["dtype"], name
+        if case["enc_type"] == "siglip":
+            assert torch.equal(y.cpu(), x)
+            continue
+        assert float((y[..., ::7, ::5].cpu() - case["sample"]).abs().max()) < 1e-5, name
+        assert float((y.cpu() - preprocess_oracle.preprocess_raw_image(x, case["enc_type"])).abs().max()) < 1e-5, name
+    # the same sequence of torch ops on the device (what the reference runs there), float input, bf16 output
+    xf = torch.rand(3, 3, 256, 256, device=DEV) * 255
+    mean = torch.tensor(preprocess_oracle.IMAGENET_DEFAULT_MEAN, device=DEV).view(1, 3, 1, 1)
+    std = torch.tensor(preprocess_oracle.IMAGENET_DEFAULT_STD, device=DEV).view(1, 3, 1, 1)
+    want = F.interpolate((xf / 255. - mean) / std, 224, mode="bicubic")
+    assert float((preprocess_raw_image(xf, "dinov2-vit-b") - want).abs().max()) < 1e-5
+    got16 = preprocess_raw_image(xf, "dinov2-vit-b", out_dtype=torch.bfloat16)
+    assert got16.dtype == torch.bfloat16 and float((got16.float() - want).abs().max()) < 2e-2
+    with pytest.raises(ValueError):
+        preprocess_raw_image(torch.zeros(1, 3, 128, 128, device=DEV), "dinov2")
