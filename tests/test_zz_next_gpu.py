@@ -97,3 +97,68 @@ def test_preprocess_raw_image_matches_reference_golden(golden):
     assert got16.dtype == torch.bfloat16 and float((got16.float() - want).abs().max()) < 2e-2
     with pytest.raises(ValueError):
         preprocess_raw_image(torch.zeros(1, 3, 128, 128, device=DEV), "dinov2")
+
+
+def _rel(a, b):
+    a, b = torch.as_tensor(a).detach().double().cpu(), torch.as_tensor(b).detach().double().cpu()
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+@pytest.mark.parametrize("config", ["multimodal", "imagenet512"])
+def test_full_size_properties_other_baseline_configs(config):
+    """BASELINE configs[3] (SiT-XL/2 with image + caption heads, text head tapped at block 16) and configs[4] (4x64x64 latents,
+    1024 tokens) at full width and a small batch: size-independent properties, as test_full_size_properties_xl2_bf16 does for
+    configs[2]."""
+    from reed_b200.image.loss import SILoss
+    from reed_b200.image.models.sit import SiT_models
+    torch.manual_seed(0)
+    if config == "multimodal":
+        size, tokens = 32, 256
+        model = SiT_models["SiT-XL/2"](input_size=32, num_classes=1000, use_cfg=True, z_dims=[768, 3584], z_types=["i", "t"],
+                                       encoder_depth=8, encoder_depth_text=16, fused_attn=True, qk_norm=False)
+        names = ["dinov2", "text_embeds_qwenvl_7b_layer_15"]
+        fn = SILoss(enc_names=names, loss_weights={names[0]: 1.0, names[1]: 0.5})
+        zs = [torch.randn(2, tokens, 768, device=DEV), torch.randn(2, 3584, device=DEV)]
+    else:
+        size, tokens = 64, 1024
+        model = SiT_models["SiT-XL/2"](input_size=64, num_classes=1000, use_cfg=True, z_dims=[768], z_types=["i"],
+                                       encoder_depth=8, fused_attn=True, qk_norm=False)
+        fn = SILoss(enc_names=["dinov2"], loss_weights={"dinov2": 1.0})
+        zs = [torch.randn(2, tokens, 768, device=DEV)]
+    model = model.to(DEV).train()
+    model.reed_precision = "bf16"
+    assert model.x_embedder.num_patches == tokens
+    x = torch.randn(2, 4, size, size, device=DEV)
+    y = torch.randint(0, 1000, (2,), device=DEV)
+    # reference init: every gate is zero -> the prediction is exactly 0 and the denoising loss is mean(target^2)
+    torch.manual_seed(1)
+    out = fn(model, x, dict(y=y), zs=zs)
+    torch.manual_seed(1)
+    torch.rand(2, 1, 1, 1)
+    noise = torch.randn_like(x)
+    assert _rel(out["denoising_loss"], ((noise - x) ** 2).flatten(1).mean(1)) < 1e-5
+    assert -1.5 <= float(out["proj_loss"]) <= 1.5
+    if config == "multimodal":
+        assert torch.is_tensor(out["text_proj_loss"]) and -1.0 <= float(out["text_proj_loss"]) <= 1.0
+        assert _rel(out["proj_loss"], out["img_proj_loss"] * 1.0 + out["text_proj_loss"] * 0.5) < 1e-4
+    else:
+        assert out["text_proj_loss"] == 0.0
+    (out["denoising_loss"].mean() + 0.5 * out["proj_loss"]).backward()
+    g = model.final_layer.linear.weight.grad
+    assert g is not None and torch.isfinite(g).all() and float(g.abs().max()) > 0
+    for proj in model.projectors:                              # both heads receive a gradient through their taps
+        assert float(proj[4].weight.grad.abs().max()) > 0
+    # the projection loss reaches the trunk up to its tap (block 8 / block 16), not beyond: gates are zero, so blocks are
+    # the identity and only the residual stream carries the gradient to the patch embedding
+    assert float(model.x_embedder.proj.weight.grad.abs().max()) > 0
+    # batch-permutation equivariance at inference with non-trivial gates
+    model.eval()
+    with torch.no_grad():
+        for lin in [b.adaLN_modulation[1] for b in model.blocks] + [model.final_layer.adaLN_modulation[1], model.final_layer.linear]:
+            lin.weight.normal_(0, 0.02)
+            lin.bias.normal_(0, 0.02)
+        tt = torch.rand(2, device=DEV)
+        p1, z1 = model(x, tt, y=y)
+        p2, _ = model(x.flip(0), tt.flip(0), y=y.flip(0))
+    assert z1 is None and p1.shape == x.shape and torch.isfinite(p1).all()
+    assert float((p1.flip(0) - p2).abs().max()) < 1e-5 * max(1.0, float(p1.abs().max()))
