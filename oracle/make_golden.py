@@ -18,7 +18,7 @@ import torch
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 REF = "/root/reference/image"
-OUT = os.path.join(os.path.dirname(HERE), "tests", "golden")
+OUT = os.environ.get("REED_GOLDEN_OUT") or os.path.join(os.path.dirname(HERE), "tests", "golden")
 
 
 def _import_reference():
