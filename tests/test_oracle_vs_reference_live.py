@@ -68,7 +68,7 @@ def test_loss_and_gradients_against_live_reference(ref, case):
     assert _rel(got["denoising_loss"], want["denoising_loss"]) < 5e-6
     for key in ("proj_loss", "img_proj_loss", "text_proj_loss"):
         w = torch.as_tensor(want[key]).double()
-        assert float((torch.as_tensor(got[key]).double() - w).abs()) < 5e-6 * max(1.0, float(w.abs())), key
+        assert float((torch.as_tensor(got[key]).detach().double() - w.detach()).abs()) < 5e-6 * max(1.0, float(w.detach().abs())), key
     for name, p in model.named_parameters():
         if p.grad is None:
             assert leaves[name].grad is None or float(leaves[name].grad.abs().max()) == 0.0, name
@@ -101,3 +101,85 @@ def test_samplers_against_live_reference(ref, patch):
     got = samplers_oracle.euler_maruyama(mine, z, y, num_steps=5, cfg_scale=2.0, guidance_high=0.6, path_type="cosine",
                                          noises=noises)
     assert float((got - want).abs().max()) < 1e-5
+
+
+def test_product_host_helpers_against_live_reference(ref):
+    """The pure-PyTorch/host pieces of the drop-in modules (they run on CPU tensors in both implementations): SILoss
+    constructor state, interpolant, time_weight, encoder_weight, the CPU time draw; sampler helper functions; model zoo."""
+    ref_sit, ref_loss, ref_samplers, _ = ref
+    from reed_b200.image import loss as my_loss, samplers as my_samplers
+    from reed_b200.image.models import sit as my_sit
+    assert my_loss.IMAGE_ENCODERS == ref_loss.IMAGE_ENCODERS
+    t = torch.rand(6, 1, 1, 1, generator=torch.Generator().manual_seed(0))
+    for path_type in ("linear", "cosine"):
+        kw = dict(path_type=path_type, enc_names=["dinov2", "t5"], loss_weights={"dinov2": 1.0, "t5": 0.5},
+                  time_schedule="cosine", cutoffs=[0.1, 0.9])
+        a, b = my_loss.SILoss(**kw), ref_loss.SILoss(**kw)
+        for attr in ("prediction", "weighting", "path_type", "enc_names", "loss_weights", "time_schedule", "cutoffs"):
+            assert getattr(a, attr) == getattr(b, attr), attr
+        for x, y in zip(a.interpolant(t), b.interpolant(t)):
+            assert torch.equal(torch.as_tensor(x), torch.as_tensor(y))
+        for sched in ("linear", "cosine", "sigmoid", "constant", "loglinear", "cutoff"):
+            assert torch.equal(a.time_weight(t, 0.7, sched, [0.25, 0.75]), b.time_weight(t, 0.7, sched, [0.25, 0.75])), sched
+        for sched in ("linear", "cosine", "sigmoid"):
+            for focus in ("text", "image"):
+                assert a.encoder_weight(1.5, 3, 10, sched, focus) == b.encoder_weight(1.5, 3, 10, sched, focus)
+    # the CPU-generator time draw of __call__ (loss.py:158-168): same stream, same values
+    for weighting, path_type in (("uniform", "linear"), ("lognormal", "linear"), ("lognormal", "cosine")):
+        mine = my_loss.SILoss(weighting=weighting, path_type=path_type, enc_names=["dinov2"], loss_weights={"dinov2": 1.0})
+        torch.manual_seed(11)
+        got = mine._sample_time(5)
+        torch.manual_seed(11)
+        want = loss_oracle.draw_time(5, weighting, path_type)
+        assert torch.equal(got, want)
+    # sampler helpers (samplers.py:5-43)
+    x = torch.randn(3, 4, 8, 8, dtype=torch.float64, generator=torch.Generator().manual_seed(1))
+    v = torch.randn(3, 4, 8, 8, dtype=torch.float64, generator=torch.Generator().manual_seed(2))
+    tt = torch.tensor([0.9, 0.5, 0.04], dtype=torch.float64)
+    assert torch.equal(my_samplers.expand_t_like_x(tt, x), ref_samplers.expand_t_like_x(tt, x))
+    assert my_samplers.compute_diffusion(0.3) == ref_samplers.compute_diffusion(0.3)
+    for path_type in ("linear", "cosine"):
+        got = my_samplers.get_score_from_velocity(v, x, tt, path_type)
+        want = ref_samplers.get_score_from_velocity(v, x, tt, path_type)
+        assert float((got - want).abs().max()) <= 1e-12 * float(want.abs().max())
+    with pytest.raises(NotImplementedError):
+        my_samplers.get_score_from_velocity(v, x, tt, "edm")
+    # zoo, helper functions and the sin-cos table
+    assert sorted(my_sit.SiT_models) == sorted(ref_sit.SiT_models)
+    import numpy as np
+    for dim, grid in ((64, 4), (1152, 16), (384, 32)):
+        assert np.array_equal(my_sit.get_2d_sincos_pos_embed(dim, grid), ref_sit.get_2d_sincos_pos_embed(dim, grid))
+    xs, sh, sc = torch.randn(2, 5, 8), torch.randn(2, 8), torch.randn(2, 8)
+    assert torch.equal(my_sit.modulate(xs, sh, sc), ref_sit.modulate(xs, sh, sc))
+    proj_a = my_sit.build_mlp(16, 32, 24)
+    proj_b = ref_sit.build_mlp(16, 32, 24)
+    assert [tuple(p.shape) for p in proj_a.parameters()] == [tuple(p.shape) for p in proj_b.parameters()]
+    assert list(proj_a.state_dict()) == list(proj_b.state_dict())
+
+
+def test_product_model_tree_against_live_reference(ref):
+    """Constructing the drop-in SiT consumes the RNG like the reference and yields the same state_dict (keys, shapes, VALUES)
+    for several zoo entries and keyword combinations; unpatchify agrees."""
+    ref_sit, _, _, _ = ref
+    from reed_b200.image.models import sit as my_sit
+    combos = [("SiT-S/2", dict(decoder_hidden_size=384, z_dims=[768], z_types=["i"], encoder_depth=8, qk_norm=False)),
+              ("SiT-S/4", dict(z_dims=[64, 32], z_types=["i", "t"], encoder_depth=4, encoder_depth_text=6, qk_norm=True)),
+              ("SiT-B/8", dict(z_dims=[128], z_types=["i"], encoder_depth=2, qk_norm=False, class_dropout_prob=0.0,
+                               num_classes=10))]
+    for name, kw in combos:
+        torch.manual_seed(5)
+        mine = my_sit.SiT_models[name](input_size=32, use_cfg=True, fused_attn=True, **kw)
+        after_mine = torch.rand(1)
+        torch.manual_seed(5)
+        theirs = ref_sit.SiT_models[name](input_size=32, use_cfg=True, fused_attn=True, **kw)
+        after_theirs = torch.rand(1)
+        assert torch.equal(after_mine, after_theirs), name                    # same number of RNG draws
+        a, b = mine.state_dict(), theirs.state_dict()
+        assert list(a) == list(b), name
+        for k in a:
+            assert a[k].shape == b[k].shape and torch.equal(a[k], b[k]), (name, k)
+        assert [n for n, p in mine.named_parameters() if not p.requires_grad] == \
+            [n for n, p in theirs.named_parameters() if not p.requires_grad]
+        tokens = mine.x_embedder.num_patches
+        y = torch.randn(2, tokens, mine.patch_size ** 2 * mine.out_channels)
+        assert torch.equal(mine.unpatchify(y), theirs.unpatchify(y)), name
