@@ -183,3 +183,38 @@ def test_product_model_tree_against_live_reference(ref):
         tokens = mine.x_embedder.num_patches
         y = torch.randn(2, tokens, mine.patch_size ** 2 * mine.out_channels)
         assert torch.equal(mine.unpatchify(y), theirs.unpatchify(y)), name
+
+
+@pytest.mark.parametrize("hyper", [dict(lr=3e-3, betas=(0.8, 0.95), eps=1e-6, weight_decay=0.05, max_norm=0.3, ema_decay=0.99),
+                                   dict(lr=1e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, max_norm=1.0, ema_decay=0.9999)])
+def test_optimizer_glue_against_torch_adamw_and_reference_ema(ref, hyper):
+    """train.py:94-105,253-259,402-412: clip_grad_norm_ -> torch.optim.AdamW -> the reference's update_ema, several steps,
+    non-default hyper-parameters included (the committed train_glue fixture holds the defaults)."""
+    from oracle import train_oracle
+    _, _, _, ns = ref
+    g = torch.Generator().manual_seed(0)
+    shapes = {"a.weight": (7, 5), "a.bias": (7,), "b.weight": (3, 7), "frozen": (4,)}
+    mod = torch.nn.ParameterDict({k.replace(".", "_"): torch.nn.Parameter(torch.randn(s, generator=g)) for k, s in shapes.items()})
+    mod["frozen"].requires_grad_(False)
+    import copy
+    ema_mod = copy.deepcopy(mod)
+    opt = torch.optim.AdamW(mod.parameters(), lr=hyper["lr"], betas=hyper["betas"], eps=hyper["eps"],
+                            weight_decay=hyper["weight_decay"])
+    params = {k: v.detach().clone() for k, v in mod.items()}
+    ema = {k: v.clone() for k, v in params.items()}
+    m1 = {k: torch.zeros_like(v) for k, v in params.items()}
+    m2 = {k: torch.zeros_like(v) for k, v in params.items()}
+    for step in range(1, 6):
+        grads = {k: torch.randn(v.shape, generator=g) * (10.0 if step == 2 else 0.1) for k, v in params.items() if k != "frozen"}
+        for k, p in mod.items():
+            p.grad = grads[k].clone() if k in grads else None
+        want_norm = torch.nn.utils.clip_grad_norm_(mod.parameters(), hyper["max_norm"])
+        opt.step()
+        ns["update_ema"](ema_mod, mod, decay=hyper["ema_decay"])
+        got_norm = train_oracle.adamw_ema_step(params, grads, m1, m2, ema, step, lr=hyper["lr"], beta1=hyper["betas"][0],
+                                               beta2=hyper["betas"][1], eps=hyper["eps"], weight_decay=hyper["weight_decay"],
+                                               max_norm=hyper["max_norm"], ema_decay=hyper["ema_decay"])
+        assert _rel(got_norm, want_norm) < 1e-6
+        for k in params:
+            assert float((params[k] - mod[k].detach()).abs().max()) < 2e-6, (step, k)
+            assert float((ema[k] - ema_mod[k].detach()).abs().max()) < 2e-6, (step, k)
