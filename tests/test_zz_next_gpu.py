@@ -162,3 +162,43 @@ def test_full_size_properties_other_baseline_configs(config):
         p2, _ = model(x.flip(0), tt.flip(0), y=y.flip(0))
     assert z1 is None and p1.shape == x.shape and torch.isfinite(p1).all()
     assert float((p1.flip(0) - p2).abs().max()) < 1e-5 * max(1.0, float(p1.abs().max()))
+
+
+@pytest.mark.parametrize("precision,loss_tol,cos_min", [("fp32", 1e-5, 0.99999), ("bf16", 2e-2, 0.999)])
+@pytest.mark.parametrize("variant", ["patch4_heads3", "patch8_qknorm"])
+def test_other_patch_sizes_match_oracle(variant, precision, loss_tol, cos_min):
+    """SiT-*/4 and */8 geometries (64 / 16 tokens, 64- / 256-wide patch vectors, head_dim 32 / 16) through the public API against
+    the CPU oracle - which tests/test_oracle_vs_reference_live.py holds to the live reference on the same architectures."""
+    import torch.nn.functional as F
+    from oracle import loss_oracle, sit_oracle
+    from reed_b200.image.loss import SILoss
+    from test_parity_gpu import _Replay, _build          # pytest puts tests/ on sys.path (rootdir-relative "prepend" import mode)
+    if variant == "patch4_heads3":
+        spec = ArchSpec(input_size=32, patch_size=4, hidden_size=96, decoder_hidden_size=96, depth=3, num_heads=3,
+                        encoder_depth=2, z_dims=[48], z_types=["i"], projector_dim=64, num_classes=1000)
+    else:
+        spec = ArchSpec(input_size=32, patch_size=8, hidden_size=64, decoder_hidden_size=64, depth=2, num_heads=4,
+                        encoder_depth=1, z_dims=[32], z_types=["i"], projector_dim=48, num_classes=1000, qk_norm=True)
+    sd = random_state(spec, 31)
+    data = random_batch(spec, 3, 32)
+    g = torch.Generator().manual_seed(33)
+    t = torch.rand((3, 1, 1, 1), generator=g)
+    noise = torch.randn(data["x"].shape, generator=g)
+    drop = torch.tensor([False, True, False])
+    model = _build(spec, sd, precision).train()
+    fn = SILoss(enc_names=["dinov2"], loss_weights={"dinov2": 1.0}, time_schedule="linear")
+    with _Replay(fn, model, t, noise, drop):
+        out = fn(model, data["x"].to(DEV), dict(y=data["y"].to(DEV)), zs=[z.to(DEV) for z in data["zs"]])
+    (out["denoising_loss"].mean() + 0.5 * out["proj_loss"]).backward()
+    leaves = {k: v.clone().requires_grad_(k != "pos_embed") for k, v in sd.items()}
+    ref = loss_oracle.si_loss(sit_oracle.as_model(leaves, spec, training=True, drop_mask=drop), data["x"], t, noise, data["zs"],
+                              enc_names=["dinov2"], loss_weights={"dinov2": 1.0}, model_kwargs=dict(y=data["y"]),
+                              time_schedule="linear")
+    (ref["denoising_loss"].mean() + 0.5 * ref["proj_loss"]).backward()
+    assert _rel(out["denoising_loss"], ref["denoising_loss"]) < loss_tol
+    assert _rel(out["proj_loss"], ref["proj_loss"]) < loss_tol
+    for name, p in model.named_parameters():
+        if p.grad is None:
+            continue
+        cos = float(F.cosine_similarity(p.grad.flatten().double().cpu(), leaves[name].grad.flatten().double(), dim=0))
+        assert cos >= cos_min, (name, cos)
