@@ -103,8 +103,25 @@ def sample_indices(n: int, rank: int, world_size: int, total_so_far: int):
     return [i * world_size + rank + total_so_far for i in range(n)]
 
 
-def load_sampling_weights(model, state_dict, strict_backbone: bool = True):
-    """generate.py:77-85: load EMA weights without the projector heads (they are not evaluated at inference)."""
+def load_legacy_checkpoints(state_dict, encoder_depth):
+    """/root/reference/image/utils.py:207-219: early checkpoints kept the blocks after the encoder tap under
+    ``decoder_blocks.{i}``; they are ``blocks.{i + encoder_depth}`` of the current model."""
+    renamed = {}
+    for key, value in state_dict.items():
+        if "decoder_blocks" in key:
+            parts = key.split(".")
+            parts[0], parts[1] = "blocks", str(int(parts[1]) + encoder_depth)
+            key = ".".join(parts)
+        renamed[key] = value
+    return renamed
+
+
+def load_sampling_weights(model, state_dict, strict_backbone: bool = True, legacy: bool = False,
+                          encoder_depth: Optional[int] = None):
+    """generate.py:77-85: load EMA weights without the projector heads (they are not evaluated at inference);
+    ``legacy`` applies ``load_legacy_checkpoints`` first (generate.py:80-83)."""
+    if legacy:
+        state_dict = load_legacy_checkpoints(state_dict, model.encoder_depth if encoder_depth is None else encoder_depth)
     sd = {k: v for k, v in state_dict.items() if "projectors" not in k}
     missing, unexpected = model.load_state_dict(sd, strict=False)
     if strict_backbone:

@@ -48,3 +48,26 @@ def test_graphed_model_refuses_train_mode_and_cpu():
     assert g.in_channels == 4 and g.projectors is m.projectors
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         g(torch.zeros(1, 4, 8, 8), torch.zeros(1), y=torch.zeros(1, dtype=torch.long))
+
+
+def test_legacy_checkpoint_keys():
+    from reed_b200.image.generate import load_legacy_checkpoints, load_sampling_weights
+    from reed_b200.image.models.sit import SiT
+    kw = dict(input_size=8, hidden_size=32, decoder_hidden_size=32, depth=3, num_heads=2, encoder_depth=1, z_dims=[16],
+              projector_dim=32, num_classes=10, qk_norm=False)
+    torch.manual_seed(0)
+    trained = SiT(**kw)
+    legacy = {}
+    for k, v in trained.state_dict().items():            # write blocks 1.. the way early checkpoints named them
+        parts = k.split(".")
+        if parts[0] == "blocks" and int(parts[1]) >= 1:
+            k = ".".join(["decoder_blocks", str(int(parts[1]) - 1)] + parts[2:])
+        legacy[k] = v
+    assert any(k.startswith("decoder_blocks.1.") for k in legacy)
+    assert list(load_legacy_checkpoints(legacy, 1)) == list(trained.state_dict())
+    torch.manual_seed(1)
+    fresh = SiT(**kw)
+    load_sampling_weights(fresh, legacy, legacy=True)
+    assert torch.equal(fresh.blocks[2].attn.qkv.weight, trained.blocks[2].attn.qkv.weight)
+    with pytest.raises(KeyError):
+        load_sampling_weights(SiT(**kw), legacy)          # without the renaming the backbone keys do not match

@@ -218,3 +218,18 @@ def test_optimizer_glue_against_torch_adamw_and_reference_ema(ref, hyper):
         for k in params:
             assert float((params[k] - mod[k].detach()).abs().max()) < 2e-6, (step, k)
             assert float((ema[k] - ema_mod[k].detach()).abs().max()) < 2e-6, (step, k)
+
+
+def test_legacy_checkpoint_renaming_against_live_reference():
+    import ast
+    from reed_b200.image.generate import load_legacy_checkpoints
+    src = open("/root/reference/image/utils.py").read()
+    ns = {}
+    for node in ast.parse(src).body:                      # utils.py itself needs timm / torchvision models: take the function only
+        if isinstance(node, ast.FunctionDef) and node.name == "load_legacy_checkpoints":
+            exec(compile(ast.Module([node], []), "utils.py", "exec"), ns)
+    sd = {"pos_embed": 1, "blocks.0.attn.qkv.weight": 2, "decoder_blocks.0.mlp.fc1.bias": 3, "decoder_blocks.19.attn.proj.weight": 4,
+          "final_layer.linear.weight": 5, "projectors.0.0.weight": 6}
+    for depth in (8, 1):
+        assert load_legacy_checkpoints(sd, depth) == ns["load_legacy_checkpoints"](sd, depth)
+        assert list(load_legacy_checkpoints(sd, depth)) == list(ns["load_legacy_checkpoints"](sd, depth))
