@@ -26,6 +26,10 @@ import os as _os
 
 # profiling knob: 0 = bias gradients of qkv / fc1 by a separate column-sum pass instead of the ones-column GEMM
 _WGRAD_BIAS = _os.environ.get("REED_WGRAD_BIAS", "1") != "0"
+# experiment (off by default, not yet run on hardware): weight-gradient GEMMs of a transformer block go to a second stream.
+# They depend only on dy and the saved activations, not on the dgrad chain, so their CTAs can fill the SMs a dgrad GEMM
+# leaves idle in its last partial round (N = 1152 shapes run 160 tiles on 74 CTA pairs: the third round is 16 % full)
+_WGRAD_STREAM = _os.environ.get("REED_WGRAD_STREAM", "0") == "1"
 _gemm_backend = BACKEND_AUTO
 _attn_backend = BACKEND_AUTO
 launch_count = 0     # kernels launched through this module (bench.py reports it as gpu_launches)
@@ -238,6 +242,43 @@ def attention_bwd(qkv, o, d_o, lse, B, T, H, hd):
 # --------------------------------------------------------------------------------------------------
 # autograd functions
 # --------------------------------------------------------------------------------------------------
+
+class _SideStream:
+    """Second stream for the weight-gradient GEMMs of one block backward (REED_WGRAD_STREAM=1, trainer mode only)."""
+    _streams = {}
+
+    def __init__(self, device):
+        key = (device.type, device.index)
+        if key not in _SideStream._streams:
+            _SideStream._streams[key] = torch.cuda.Stream(device=device)
+        self.stream = _SideStream._streams[key]
+        self.keep = []            # operands stay referenced until the join: the allocator must not hand them out meanwhile
+        self.used = False
+
+    def run(self, fn, *operands):
+        """Enqueue fn() on the side stream behind everything the current stream has enqueued so far."""
+        ready = torch.cuda.Event()
+        ready.record(torch.cuda.current_stream())
+        self.stream.wait_event(ready)
+        with torch.cuda.stream(self.stream):
+            out = fn()
+        self.keep.extend(operands)
+        self.used = True
+        return out
+
+    def join(self):
+        if self.used:
+            done = torch.cuda.Event()
+            done.record(self.stream)
+            torch.cuda.current_stream().wait_event(done)
+        self.keep.clear()
+        self.used = False
+
+
+def _flat_grads(*params):
+    """True when a trainer owns flat gradient storage for every given parameter (the kernels write there, autograd sees None)."""
+    return all(p is None or getattr(p, "_reed_main_grad", None) is not None for p in params)
+
 
 def _weight_grad(p, dy2d, x2d):
     """dW[N,K] = dy^T x written into the trainer's flat gradient when present; returns what autograd should see."""
@@ -516,14 +557,19 @@ class SiTBlockFn(torch.autograd.Function):
         # ---- MLP branch:  x2 = x1 + g_m * (gelu(xm2 W1^T + b1) W2^T + b2)
         db2_buf, db2 = bias_buffer(b_fc2)
         dy2 = gate_bwd(dx2, y2, g_m, T, dg_m, db2_buf)
-        dw2 = _weight_grad(w_fc2, dy2, a)
+        side = _SideStream(dx2.device) if (_WGRAD_STREAM and _flat_grads(w_fc2, w_fc1, b_fc1, w_proj, w_qkv, b_qkv, w_ada)) else None
+
+        def off_stream(fn, *operands):
+            return side.run(fn, *operands) if side is not None else fn()
+
+        dw2 = off_stream(lambda: _weight_grad(w_fc2, dy2, a), dy2, a)
         dh = gemm(dy2, W(w_fc2), b_mn=True, out_dtype=act_dtype, epilogue=EPI_DGELU, aux=h)
-        dw1, db1 = _weight_and_bias_grad(w_fc1, b_fc1, dh, xm2, xm2_ext)
+        dw1, db1 = off_stream(lambda: _weight_and_bias_grad(w_fc1, b_fc1, dh, xm2, xm2_ext), dh, xm2s)
         dxm2 = gemm(dh, W(w_fc1), b_mn=True, out_dtype=act_dtype)
         # ---- attention branch:  x1 = x0 + g_a * (attn(xm1) Wp^T + bp); its gate backward rides on the LN backward
         dbp_buf, dbp = bias_buffer(b_proj)
         dx1, dy1 = ln_modulate_gate_bwd(dxm2, x1, mean2, rstd2, sc_m, T, dx2, dsh_m, dsc_m, y1, g_a, dg_a, dbp_buf)
-        dwp = _weight_grad(w_proj, dy1, o)
+        dwp = off_stream(lambda: _weight_grad(w_proj, dy1, o), dy1, o)
         d_o = gemm(dy1, W(w_proj), b_mn=True, out_dtype=act_dtype)
         dqkv = attention_bwd(qkv, o, d_o, lse, B, T, H, hd)
         qk_grads = (None, None, None, None)
@@ -537,14 +583,14 @@ class SiTBlockFn(torch.autograd.Function):
             dqkv = qk_norm_bwd(dqkv, qkv_raw, qk_stats, qn_w.detach().float(), kn_w.detach().float(), bufs[0], bufs[1],
                                bufs[2], bufs[3], M, H, hd)
             qk_grads = tuple(rets)
-        dwqkv, dbqkv = _weight_and_bias_grad(w_qkv, b_qkv, dqkv, xm1, xm1_ext)
+        dwqkv, dbqkv = off_stream(lambda: _weight_and_bias_grad(w_qkv, b_qkv, dqkv, xm1, xm1_ext), dqkv, xm1s)
         dxm1 = gemm(dqkv, W(w_qkv), b_mn=True, out_dtype=act_dtype)
         dx0 = ln_modulate_bwd(dxm1, x0, mean1, rstd1, sc_a, T, dx1, dsh_a, dsc_a)
 
         # ---- adaLN linear:  mod = c_act W_ada^T + b_ada
         dmod_a = cast(dmod, act_dtype)
         db_ada = _bias_grad(b_ada, dmod)
-        dw_ada = _weight_grad(w_ada, dmod_a, c_act)
+        dw_ada = off_stream(lambda: _weight_grad(w_ada, dmod_a, c_act), dmod_a, c_act)
         dc = None
         if ctx.needs_input_grad[1]:
             if ctx.c_acc is not None:     # [B, 6D] x [6D, D]: few rows, long reduction -> split-K slices add into the side buffer
@@ -552,6 +598,8 @@ class SiTBlockFn(torch.autograd.Function):
             else:
                 dc = gemm(dmod_a, W(w_ada), b_mn=True, out_dtype=act_dtype)
 
+        if side is not None:
+            side.join()                       # the bucket's gradients are complete on the current stream from here on
         if ctx.after_backward is not None:
             ctx.after_backward()
         return (dx0.view(B, T, D), dc, dw_ada, db_ada, dwqkv, dbqkv, dwp, dbp, dw1, db1, dw2, db2, None, None, None, None) + qk_grads
