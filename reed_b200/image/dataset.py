@@ -152,18 +152,24 @@ class _Staging:
 class LatentBatchLoader:
     """Iterates ``(moments [B,2C,S,S], labels [B], text_embeds or None)`` device batches from a ``CustomDataset``.
 
-    Sampling order follows ``DataLoader(shuffle=True, drop_last=True)`` semantics (a fresh ``torch.randperm`` of the
-    rank's shard per epoch from ``generator``); ranks take disjoint strided shards like accelerate's sharded sampler.
+    Sampling order follows ``DataLoader(shuffle=True, drop_last=True)`` semantics: a fresh ``torch.randperm`` of the
+    whole dataset per epoch, of which the ranks take disjoint strided shards like accelerate's sharded sampler.  The
+    permutation must be THE SAME on every rank for the shards to be disjoint, so it is drawn from a private generator
+    seeded ``seed + epoch`` (accelerate synchronises the sampler's RNG across ranks to the same end) - never from the
+    global CPU generator, which ``train.py:176`` seeds differently per rank and which SILoss draws its times from.  A
+    caller-supplied ``generator`` is used as is: with ``world > 1`` it has to be seeded identically on all ranks.
     Each batch is collated into one of ``depth`` pinned staging slots and copied on ``copy_stream``; the consumer's
     stream waits on the slot's event, so the copy of batch i+1 overlaps the compute of batch i.  The device tensors of a
     slot are reused ``depth`` batches later - consume (or clone) a batch before asking for ``depth`` more.
     """
 
     def __init__(self, dataset, batch_size: int, device, *, rank: int = 0, world: int = 1, shuffle: bool = True,
-                 generator: Optional[torch.Generator] = None, depth: int = 2, with_text: Optional[bool] = None):
+                 generator: Optional[torch.Generator] = None, depth: int = 2, with_text: Optional[bool] = None,
+                 seed: int = 0):
         self.dataset, self.batch_size, self.device = dataset, batch_size, torch.device(device)
         self.rank, self.world, self.shuffle, self.depth = rank, world, shuffle, max(2, depth)
         self.generator = generator
+        self.seed, self.epoch = int(seed), 0
         self.with_text = (getattr(dataset, "text_embeds_dir", None) is not None) if with_text is None else with_text
         self.cuda = self.device.type == "cuda"
         self._slots: List[_Staging] = []
@@ -174,7 +180,11 @@ class LatentBatchLoader:
 
     def epoch_indices(self) -> List[int]:
         n = len(self.dataset)
-        order = torch.randperm(n, generator=self.generator).tolist() if self.shuffle else list(range(n))
+        gen = self.generator
+        if gen is None:
+            gen = torch.Generator().manual_seed(self.seed + self.epoch)
+        self.epoch += 1
+        order = torch.randperm(n, generator=gen).tolist() if self.shuffle else list(range(n))
         shard = order[self.rank::self.world][: (n // self.world)]
         usable = len(shard) // self.batch_size * self.batch_size
         return shard[:usable]

@@ -26,6 +26,7 @@ from typing import Dict, Optional
 import numpy as np
 import torch
 
+from .. import ops
 from .samplers import euler_maruyama_sampler, euler_sampler
 
 
@@ -64,6 +65,7 @@ class GraphedSiT:
         with torch.no_grad(), torch.cuda.graph(graph):
             g["pred"] = self.model(g["x"], g["t"], y=g["y"])[0]
         g["graph"] = graph
+        g["epoch"] = ops.weights_epoch
         return g
 
     def __call__(self, x, t, y=None, inference=True):
@@ -75,6 +77,11 @@ class GraphedSiT:
         g = self._graphs.get(key)
         if g is None:
             g = self._graphs[key] = self._capture(x, t, y)
+        if g["epoch"] != ops.weights_epoch:
+            # the weights were rewritten since the capture (a train step updated the EMA this model is): the graph
+            # reads the bf16 shadows through baked-in pointers, so re-cast them in place before replaying
+            ops.refresh_shadows(self.model)
+            g["epoch"] = ops.weights_epoch
         g["x"].copy_(x)
         g["t"].copy_(t)
         g["y"].copy_(y)

@@ -85,9 +85,9 @@ class SILoss:
         elif schedule == "loglinear":
             scale = 1 - torch.log(t + 1)
         elif schedule == "cutoff":
-            scale = torch.ones_like(t)
-            scale[t < cutoffs[0]] = 0
-            scale[t > cutoffs[1]] = 0
+            # same values as the reference's masked assignments (loss.py:145-147), without index_put: that needs a
+            # device sync and cannot be captured in a CUDA graph
+            scale = ((t >= cutoffs[0]) & (t <= cutoffs[1])).to(t.dtype)
         else:
             raise ValueError("Invalid schedule. Choose from 'linear', 'cosine', 'sigmoid'.")
         return base_weight * scale

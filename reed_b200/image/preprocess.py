@@ -2,9 +2,9 @@
 (/root/reference/image/train.py:53-74), one fused kernel (``reed_preprocess_image``) instead of divide / Normalize /
 ``F.interpolate(mode='bicubic')``.
 
-This is the first half of SURVEY 8(f) row 3; the encoder forward itself (DINOv2 from torch.hub, absent here) is not
-part of this package.  The kernel has not run on hardware yet (written after round 1's GPU minutes were spent); its
-formula is pinned on the CPU by ``oracle/preprocess_oracle.py`` against the reference function.
+This is the first half of SURVEY 8(f) row 3 (the encoder forward is ``reed_b200.image.encoders``).  The formula is pinned
+on the CPU by ``oracle/preprocess_oracle.py`` against the reference function; the kernel is checked against it on the B200
+(tests/test_zz_next_gpu.py).
 """
 from __future__ import annotations
 
@@ -29,7 +29,7 @@ def _plan(enc_type: str, resolution: int):
         return IMAGENET_DEFAULT_MEAN, IMAGENET_DEFAULT_STD, resolution, 0
     if "dinov2" in enc_type:
         return IMAGENET_DEFAULT_MEAN, IMAGENET_DEFAULT_STD, resized, 0
-    if "dinov1" == enc_type:
+    if "dinov1" in enc_type:                                      # train.py:66
         return IMAGENET_DEFAULT_MEAN, IMAGENET_DEFAULT_STD, resolution, 0
     if "jepa" in enc_type:
         return IMAGENET_DEFAULT_MEAN, IMAGENET_DEFAULT_STD, resized, 0
@@ -43,8 +43,8 @@ def preprocess_raw_image(x: torch.Tensor, enc_type: str, out_dtype: torch.dtype 
         return x
     if not x.is_cuda:
         raise RuntimeError("reed_b200 preprocess_raw_image runs on CUDA (sm_100a) tensors only; there is no CPU fallback")
-    if x.dim() != 4 or x.shape[-1] != x.shape[-2] or x.shape[1] > 4:
-        raise ValueError("expected a [B, C<=4, R, R] image batch")
+    if x.dim() != 4 or x.shape[-1] != x.shape[-2] or x.shape[1] != 3:
+        raise ValueError("expected a [B, 3, R, R] image batch (the normalisation constants are per RGB channel)")
     mean, std, out_size, resize_first = plan
     if out_size < 1:
         raise ValueError(f"resolution {x.shape[-1]} is below 256: the reference resizes to 224 * (resolution // 256) = 0")

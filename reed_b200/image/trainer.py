@@ -134,6 +134,7 @@ class FlatState:
                     sview.copy_(p.data)
                     p._reed_shadow = sview
                     p._reed_shadow_version = p._version
+                    p._reed_shadow_managed = True       # reed_adamw_ema rewrites it together with the master
                 if ema is not None:
                     ep = ema_params[name]
                     eview = b.ema[off:off + n].view(p.shape)
@@ -236,6 +237,8 @@ class GradientReducer:
 class ReedTrainer:
     """loss -> backward (+ overlapped all-reduce) -> clip -> AdamW -> EMA, one call per optimizer step."""
 
+    _STAGING_ROWS = 4      # pinned rows for the graphed step's host-side inputs (how far the host may run ahead)
+
     def __init__(self, model: nn.Module, loss_fn, *, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0,
                  max_grad_norm=1.0, ema_decay=0.9999, proj_coeff=0.5, precision: Optional[str] = "bf16", group=None,
                  with_ema=True, comm_sms: int = 16, shard_optimizer: bool = False, nvls: bool = False):
@@ -321,6 +324,7 @@ class ReedTrainer:
     def optimizer_step(self, device_step=False):
         """device_step: read the step from the device counter (incremented here by a kernel) instead of passing the
         host integer - the form a CUDA graph can replay."""
+        ops.bump_weights_epoch()               # masters and EMA change behind autograd's back: lazily made shadows are stale
         if self.shard:
             return self._optimizer_step_sharded(device_step)
         self.step_count += 1
@@ -523,6 +527,7 @@ class ReedTrainer:
             for p in b.params:
                 if getattr(p, "_reed_shadow", None) is not None:
                     p._reed_shadow_version = p._version
+        ops.bump_weights_epoch()
         return int(ckpt.get("steps", step))
 
     def train_step(self, images, labels, zs, diffusion_decay=1.0, repa_decay=1.0):
@@ -583,7 +588,11 @@ class ReedTrainer:
         g = {"images": images.clone(), "labels": labels.clone(), "zs": [z.clone() for z in zs],
              "time": torch.zeros((images.shape[0], 1, 1, 1), device=dev, dtype=torch.float32),
              "scalars": torch.ones(2, device=dev, dtype=torch.float32),
-             "host": torch.zeros(images.shape[0] + 2, dtype=torch.float32).pin_memory()}
+             # ring of pinned staging rows for the per-step host values (time draws + 2 curriculum scalars): a row is
+             # rewritten only after the H2D copies that read it have executed (event fence) - the host may run several
+             # replays ahead of the device
+             "host": [torch.zeros(images.shape[0] + 2, dtype=torch.float32).pin_memory() for _ in range(self._STAGING_ROWS)],
+             "host_done": [None] * self._STAGING_ROWS, "host_next": 0}
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
@@ -605,18 +614,25 @@ class ReedTrainer:
         """Replay the captured step on a new batch.  Returns (loss, out) as views of the graph's static outputs."""
         assert self._graph is not None, "call capture() first"
         g = self._g
-        host = g["host"]
+        row = g["host_next"]
+        g["host_next"] = (row + 1) % self._STAGING_ROWS
+        if g["host_done"][row] is not None:
+            g["host_done"][row].synchronize()                       # the copies issued _STAGING_ROWS replays ago have run
+        host = g["host"][row]
         bsz = images.shape[0]
         host[:bsz] = self.loss_fn._sample_time(bsz).flatten()       # the draw SILoss would make (CPU generator)
         host[bsz] = diffusion_decay
         host[bsz + 1] = repa_decay
         g["time"].view(-1).copy_(host[:bsz], non_blocking=True)
         g["scalars"].copy_(host[bsz:], non_blocking=True)
+        g["host_done"][row] = torch.cuda.Event()
+        g["host_done"][row].record(torch.cuda.current_stream(images.device))
         g["images"].copy_(images, non_blocking=True)
         g["labels"].copy_(labels, non_blocking=True)
         for dst, src in zip(g["zs"], zs):
             dst.copy_(src, non_blocking=True)
         self._graph.replay()
+        ops.bump_weights_epoch()
         self._state_complete = not self.shard
         self.step_count += 1
         return g["loss"], g["out"]

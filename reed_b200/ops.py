@@ -87,13 +87,25 @@ def cast(x: torch.Tensor, dtype: torch.dtype, op: int = 0) -> torch.Tensor:
     return out
 
 
+# Bumped by whoever rewrites parameter storage through raw pointers (the fused clip/AdamW/EMA kernels, graph replays of
+# the train step, checkpoint loads): tensor._version does not see those writes, so lazily created bf16 shadows - the EMA
+# model's, above all - are also keyed on this counter.  Shadows the optimizer kernel itself refreshes are "managed".
+weights_epoch = 0
+
+
+def bump_weights_epoch():
+    global weights_epoch
+    weights_epoch += 1
+
+
 def weight_for(p: torch.Tensor, act_dtype: torch.dtype) -> torch.Tensor:
     """The tensor the GEMM reads for parameter ``p``: the fp32 master, or its bf16 shadow (refreshed when stale)."""
     w = p.detach()
     if act_dtype == torch.float32:
         return w
     shadow = getattr(p, "_reed_shadow", None)
-    if shadow is not None and getattr(p, "_reed_shadow_version", -1) == p._version and shadow.device == p.device:
+    if (shadow is not None and getattr(p, "_reed_shadow_version", -1) == p._version and shadow.device == p.device
+            and (getattr(p, "_reed_shadow_managed", False) or getattr(p, "_reed_shadow_epoch", -1) == weights_epoch)):
         return shadow
     w = w.contiguous()
     if shadow is None or shadow.shape != w.shape or shadow.device != w.device:
@@ -101,7 +113,22 @@ def weight_for(p: torch.Tensor, act_dtype: torch.dtype) -> torch.Tensor:
     _launch("reed_unary", _p(w), F32, _p(shadow), BF16, 0, w.numel(), _stream())
     p._reed_shadow = shadow
     p._reed_shadow_version = p._version
+    p._reed_shadow_epoch = weights_epoch
     return shadow
+
+
+def refresh_shadows(module) -> int:
+    """Re-cast (in place, same storage) every stale bf16 shadow of ``module``'s parameters; returns how many were stale.
+    CUDA graphs that baked shadow pointers in (generate.GraphedSiT) call this before a replay."""
+    n = 0
+    for p in module.parameters():
+        if getattr(p, "_reed_shadow", None) is None:
+            continue
+        before = p._reed_shadow
+        launched = launch_count
+        assert weight_for(p, torch.bfloat16) is before, "a shadow changed storage: graphs holding its pointer are invalid"
+        n += launch_count - launched
+    return n
 
 
 def _grad_target(p: torch.Tensor):

@@ -13,8 +13,6 @@ GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
-    config.addinivalue_line("markers", "gpu_next: GPU test written after the round's GPU budget was spent - not yet run on a "
-                                       "B200, kept out of `-m gpu` until it has been (then re-marked gpu)")
 
 
 def pytest_collection_modifyitems(config, items):
@@ -22,7 +20,7 @@ def pytest_collection_modifyitems(config, items):
         return
     skip = pytest.mark.skip(reason="no CUDA device")
     for item in items:
-        if "gpu" in item.keywords or "gpu_next" in item.keywords:
+        if "gpu" in item.keywords:
             item.add_marker(skip)
 
 

@@ -102,3 +102,27 @@ def test_sample_posterior_refuses_cpu_tensors():
     from reed_b200.image.dataset import sample_posterior
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         sample_posterior(torch.zeros(1, 8, 4, 4))
+
+
+def test_default_shuffle_gives_disjoint_shards_and_leaves_the_global_generator_alone(tmp_path):
+    """Without a caller generator every rank must still stride THE SAME permutation (seed + epoch), and the draw must not
+    advance the global CPU generator SILoss takes its time draws from (each rank seeds that one differently, train.py:176)."""
+    from reed_b200.image.dataset import CustomDataset, LatentBatchLoader
+    root = _make_tree(str(tmp_path), n=20, text_dir=None)
+    ds = CustomDataset(root, load_images=False)
+    loaders = [LatentBatchLoader(ds, 2, "cpu", rank=r, world=4, seed=11) for r in range(4)]
+    for epoch in range(3):
+        shards = []
+        for r, ld in enumerate(loaders):
+            torch.manual_seed(100 + r)                            # per-rank global seed, as the reference does
+            before = torch.get_rng_state()
+            shards.append(ld.epoch_indices())
+            assert torch.equal(torch.get_rng_state(), before)
+        flat = [i for s in shards for i in s]
+        assert len(flat) == len(set(flat)) == 16                  # 20 // 4 = 5 per rank -> 2 batches of 2
+        if epoch == 0:
+            first = shards
+        else:
+            assert shards != first                                # a fresh permutation per epoch
+    again = LatentBatchLoader(ds, 2, "cpu", rank=2, world=4, seed=11).epoch_indices()
+    assert again == first[2]

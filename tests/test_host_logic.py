@@ -162,3 +162,51 @@ def test_argument_errors_are_reported_without_a_device(built):
     # zero-sized work returns before touching the device as well
     built.call("reed_sample_posterior", None, None, None, None, 1.0, 0.0, None, 0, 4, 16, None)
     built.call("reed_grad_sumsq", None, 0, None, None)
+
+
+def test_cutoff_schedule_equals_reference_masked_assignment():
+    """time_weight('cutoff') without index_put (graph-capturable) gives the reference's values (loss.py:143-147)."""
+    from reed_b200.image.loss import SILoss
+    fn = SILoss(enc_names=["dinov2"], loss_weights={"dinov2": 1.0})
+    t = torch.tensor([0.0, 0.1, 0.2, 0.5, 0.8, 0.81, 1.0]).view(-1, 1, 1, 1)
+    want = torch.ones_like(t)
+    want[t < 0.2] = 0
+    want[t > 0.8] = 0
+    got = fn.time_weight(t, 0.7, "cutoff", [0.2, 0.8])
+    assert got.shape == t.shape and torch.equal(got, 0.7 * want)
+
+
+def test_lazy_shadows_are_keyed_on_the_weights_epoch(monkeypatch):
+    """A bf16 shadow made lazily by weight_for goes stale when a kernel rewrites the master through its raw pointer
+    (tensor._version does not move): the weights epoch invalidates it; optimizer-managed shadows stay valid."""
+    from reed_b200 import ops
+    casts = []
+
+    def fake_launch(name, *args, n=1):
+        casts.append(name)
+        ops.launch_count += n
+    monkeypatch.setattr(ops, "_launch", fake_launch)
+    monkeypatch.setattr(ops, "_stream", lambda: 0)
+    p = torch.nn.Parameter(torch.randn(4, 8))
+    s1 = ops.weight_for(p, torch.bfloat16)
+    assert casts == ["reed_unary"] and ops.weight_for(p, torch.bfloat16) is s1 and len(casts) == 1
+    ops.bump_weights_epoch()
+    assert ops.weight_for(p, torch.bfloat16) is s1 and len(casts) == 2          # re-cast, same storage
+    p._reed_shadow_managed = True
+    ops.bump_weights_epoch()
+    assert ops.weight_for(p, torch.bfloat16) is s1 and len(casts) == 2          # managed: the optimizer keeps it fresh
+    p._reed_shadow_managed = False
+    m = torch.nn.Linear(8, 4)
+    assert ops.refresh_shadows(m) == 0                                          # no shadows yet: nothing to do
+    ops.weight_for(m.weight, torch.bfloat16)
+    ops.bump_weights_epoch()
+    assert ops.refresh_shadows(m) == 1 and ops.refresh_shadows(m) == 0
+    assert ops.weight_for(p, torch.float32).data_ptr() == p.data_ptr()
+
+
+def test_preprocess_plan_matches_reference_substring_rules():
+    from reed_b200.image.preprocess import _plan, preprocess_raw_image
+    assert _plan("dinov1-vit-b", 256) is not None and _plan("dinov1", 256)[2] == 256      # train.py:66 `'dinov1' in enc_type`
+    assert _plan("dinov2-vit-b", 512)[2] == 448 and _plan("sam", 256) is None
+    x = torch.zeros(1, 3, 8, 8)
+    assert preprocess_raw_image(x, "sam") is x

@@ -40,7 +40,7 @@ def test_product_plan_and_cpu_refusal():
     assert preprocess._plan("dinov2-vit-l", 512)[2] == 448
     assert preprocess._plan("clip-vit-L", 256)[3] == 1 and preprocess._plan("clip-vit-L", 256)[0] == preprocess.CLIP_DEFAULT_MEAN
     assert preprocess._plan("mocov3-vit-b", 256)[2] == 256 and preprocess._plan("dinov1", 256)[2] == 256
-    assert preprocess._plan("dinov1-vit-b", 256) is None            # the reference compares 'dinov1' == enc_type (train.py:66)
+    assert preprocess._plan("dinov1-vit-b", 256)[2] == 256          # the reference tests `'dinov1' in enc_type` (train.py:66)
     assert preprocess._plan("siglip", 256) is None
     x = torch.zeros(1, 3, 256, 256, dtype=torch.uint8)
     assert preprocess.preprocess_raw_image(x, "siglip") is x

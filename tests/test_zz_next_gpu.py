@@ -1,13 +1,12 @@
-"""GPU tests of features added after round 1's GPU minutes were spent.  They are marked ``gpu_next`` (NOT ``gpu``): they
-have never run on a B200, so they stay out of the `-m gpu` suite until the first GPU call of round 2 has run them
-(`python -m pytest tests/test_zz_next_gpu.py -m gpu_next`), after which they move to ``gpu``."""
+"""GPU tests of gradient accumulation, the preprocessing kernel, the other BASELINE configs' size-independent properties
+and the SiT-*/4, */8 geometries.  Written at the end of round 1, first run on a B200 in round 2 (profiles/r02_tests_gpu.txt)."""
 import pytest
 import torch
 
 from oracle.fixtures import random_batch, random_state
 from oracle.sit_oracle import ArchSpec
 
-pytestmark = pytest.mark.gpu_next
+pytestmark = pytest.mark.gpu
 DEV = "cuda"
 
 
@@ -199,6 +198,10 @@ def test_other_patch_sizes_match_oracle(variant, precision, loss_tol, cos_min):
     assert _rel(out["proj_loss"], ref["proj_loss"]) < loss_tol
     for name, p in model.named_parameters():
         if p.grad is None:
+            continue
+        if float(leaves[name].grad.norm()) < 1e-6:
+            # exactly zero in exact arithmetic (k_norm.bias shifts every logit of a row by the same q.b): noise only
+            assert float(p.grad.norm()) < (1e-5 if precision == "fp32" else 1e-2), name
             continue
         cos = float(F.cosine_similarity(p.grad.flatten().double().cpu(), leaves[name].grad.flatten().double(), dim=0))
         assert cos >= cos_min, (name, cos)

@@ -192,3 +192,87 @@ def test_sample_latents_driver(tmp_path):
     assert files == ["latents-rank0-00000.npz", "latents-rank0-00001.npz"]
     first = np.load(os.path.join(tmp_path, files[0]))
     assert np.array_equal(first["latents"], lat0[:2].numpy()) and first["indices"].tolist() == [0, 2]
+
+
+def _tiny_trainer(precision="bf16", seed=11):
+    from reed_b200.image.loss import SILoss
+    from reed_b200.image.models.sit import SiT
+    from reed_b200.image.trainer import ReedTrainer
+    spec = ArchSpec(input_size=16, hidden_size=128, decoder_hidden_size=128, depth=2, num_heads=2, encoder_depth=1,
+                    z_dims=[64], projector_dim=128)
+    m = SiT(path_type="linear", use_cfg=True, input_size=16, hidden_size=128, decoder_hidden_size=128, depth=2, num_heads=2,
+            encoder_depth=1, z_dims=[64], z_types=["i"], projector_dim=128, num_classes=1000, fused_attn=True, qk_norm=False)
+    m.load_state_dict(random_state(spec, seed))
+    m = m.to(DEV).train()
+    return spec, ReedTrainer(m, SILoss(enc_names=["dinov2"], loss_weights={"dinov2": 1.0}), precision=precision,
+                             ema_decay=0.5)
+
+
+@pytest.mark.parametrize("graphed_eval", [False, True])
+def test_ema_inference_in_bf16_follows_the_training_steps(graphed_eval):
+    """The fused optimizer updates the EMA through raw pointers; bf16 evaluations of the EMA model must see the weights of
+    the LATEST step, not the bf16 copies made at its first evaluation (also through GraphedSiT's baked-in pointers)."""
+    from reed_b200 import ops
+    from reed_b200.image.generate import GraphedSiT
+    spec, tr = _tiny_trainer("bf16")
+    to_dev = lambda d: (d["x"].to(DEV), d["y"].to(DEV), [z.to(DEV) for z in d["zs"]])
+    x = torch.randn(4, 4, 16, 16, device=DEV)
+    t = torch.rand(4, device=DEV)
+    y = torch.randint(0, 1000, (4,), device=DEV)
+    runner = GraphedSiT(tr.ema) if graphed_eval else tr.ema
+    with torch.no_grad():
+        first = runner(x, t, y=y)[0].clone()
+    for i in range(3):
+        tr.train_step(*to_dev(random_batch(spec, 4, 50 + i)))
+    with torch.no_grad():
+        later = runner(x, t, y=y)[0].clone()
+        # a fresh bf16 recast of the current fp32 EMA: what the evaluation has to equal
+        fresh = type(tr.ema)(**{k: getattr(spec, k) for k in ("input_size", "hidden_size", "decoder_hidden_size", "depth",
+                                                              "num_heads", "encoder_depth", "projector_dim")},
+                             path_type="linear", use_cfg=True, z_dims=[64], z_types=["i"], num_classes=1000,
+                             fused_attn=True, qk_norm=False).to(DEV).eval()
+        fresh.load_state_dict(tr.ema.state_dict())
+        fresh.reed_precision = "bf16"
+        want = fresh(x, t, y=y)[0]
+    assert float((later - first).abs().max()) > 1e-3           # ema_decay 0.5: three steps move the EMA visibly
+    assert torch.equal(later, want)
+    assert ops.weights_epoch >= 3
+
+
+def test_graphed_step_staging_survives_host_run_ahead():
+    """train_step_graphed called 8 times with no host/device sync in between: every replay must consume ITS OWN time draws
+    and curriculum scalars (ring of pinned rows fenced by events), whatever the host writes meanwhile."""
+    spec, tr = _tiny_trainer("bf16")
+    to_dev = lambda d: (d["x"].to(DEV), d["y"].to(DEV), [z.to(DEV) for z in d["zs"]])
+    batch = to_dev(random_batch(spec, 4, 60))
+    tr.capture(*batch, warmup=2)
+    g = tr._g
+    # slow the device down so the host really is several replays ahead
+    ballast = torch.randn(4096, 4096, device=DEV)
+    torch.manual_seed(321)
+    seen_t, seen_s = [], []
+    for i in range(8):
+        for _ in range(4):
+            ballast = ballast @ ballast * 1e-4
+        tr.train_step_graphed(*batch, diffusion_decay=0.1 * (i + 1), repa_decay=1.0 - 0.05 * i)
+        seen_t.append(g["time"].clone())                        # stream-ordered: after replay i, before step i+1's copies
+        seen_s.append(g["scalars"].clone())
+    torch.cuda.synchronize()
+    torch.manual_seed(321)
+    for i in range(8):
+        want_t = torch.rand((4, 1, 1, 1))
+        assert torch.equal(seen_t[i].cpu(), want_t), i
+        assert torch.allclose(seen_s[i].cpu(), torch.tensor([0.1 * (i + 1), 1.0 - 0.05 * i])), i
+    assert len({id(r) for r in g["host"]}) == tr._STAGING_ROWS >= 2
+
+
+def test_cutoff_schedule_is_graph_capturable():
+    from reed_b200.image.loss import SILoss
+    from reed_b200.image.trainer import ReedTrainer
+    spec, tr = _tiny_trainer("bf16")
+    tr.loss_fn = SILoss(enc_names=["dinov2"], loss_weights={"dinov2": 1.0}, time_schedule="cutoff", cutoffs=[0.2, 0.8])
+    to_dev = lambda d: (d["x"].to(DEV), d["y"].to(DEV), [z.to(DEV) for z in d["zs"]])
+    batch = to_dev(random_batch(spec, 4, 61))
+    tr.capture(*batch, warmup=1)
+    loss, _ = tr.train_step_graphed(*batch)
+    assert torch.isfinite(loss)
