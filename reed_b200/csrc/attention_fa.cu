@@ -16,11 +16,12 @@
 //   * warps 0-3 / 4-7 = softmax group of tile 0 / 1 (thread = query row = TMEM lane).  Online softmax in the exp2 domain
 //     with a LAZY running maximum: the reference maximum of a row only moves when a block's maximum exceeds it by more
 //     than 8 (P <= 2^8, exact in fp32 / bf16 range), so the O_i rescale (TMEM load-multiply-store) is rare; the final
-//     normalisation uses the same reference, so the result is the exact softmax.  Two passes over the S row in TMEM
-//     (max, then exp + pack) keep the live registers at 32 scores + 16 packed words: no spills.
+//     normalisation uses the same reference, so the result is the exact softmax.  The row sum l = sum_k P is a sixteenth
+//     ... an extra N = 16 MMA per k-step against a constant ones tile (O[:, hd'] += P . 1): 128 adds per row leave the
+//     MUFU-bound softmax warps for the tensor pipe, and l is built from the same bf16 P the numerator uses.
 //   * epilogue per tile: O_i / l -> bf16 -> swizzled staging tile -> TMA store; lse = (m + log2 l) ln 2.
 //
-// TMEM map (512 columns): S_0/P_0 0..127 | S_1/P_1 128..255 | O_0 256..335 | O_1 384..463.
+// TMEM map (512 columns): S_0/P_0 0..127 | S_1/P_1 128..255 | O_0 256..335, row sum 336 | O_1 384..463, row sum 464.
 #include <cuda.h>
 #include "attention_fa.cuh"
 
@@ -40,7 +41,8 @@ struct FwdCfg {
   static constexpr int kOffQ = 0;                                     // [2 sets][2 tiles]
   static constexpr int kOffOut = 4 * TL::kBytes;                      // [2 tiles] output staging
   static constexpr int kOffKV = 6 * TL::kBytes;
-  static constexpr int kOffBar = kOffKV + kStages * TL::kBytes;
+  static constexpr int kOffOnes = kOffKV + kStages * TL::kBytes;      // [16 keys x 16] SWIZZLE_32B tile, column 0 = 1
+  static constexpr int kOffBar = kOffOnes + 1024;
   // barriers: q_full[4] q_empty[4] kv_full[S] kv_empty[S] s_full[2] p_full[2] o_full[2]
   static constexpr int kNumBars = 8 + 2 * kStages + 6;
   static constexpr int kTotal = 1024 + kOffBar + kNumBars * 8 + 16;
@@ -84,6 +86,12 @@ attn_fa_fwd_kernel(const __grid_constant__ AttnMaps maps, float* __restrict__ ls
       mbar_init(o_full + i, 1);
     }
     fence_barrier_init();
+    // the ones tile of the row-sum MMA: every k-step (16 keys) reads the same 512 bytes; row r = 32 bytes, its first
+    // 16-byte chunk sits at (r >> 2 & 1) * 16 under SWIZZLE_32B
+    uint32_t* ones = reinterpret_cast<uint32_t*>(smem + CF::kOffOnes);
+    for (int w = 0; w < 128; ++w) ones[w] = 0u;
+    for (int r = 0; r < 16; ++r) ones[r * 8 + ((r >> 2) & 1) * 4] = 0x00003F80u;      // bf16 1.0 in element 0
+    fence_proxy_async();
     tma_prefetch_desc(&maps.qkv_main);
     tma_prefetch_desc(&maps.out_main);
     if (TL::kTail) {
@@ -163,7 +171,7 @@ attn_fa_fwd_kernel(const __grid_constant__ AttnMaps maps, float* __restrict__ ls
         if (i == 0) mbar_wait(&kv_full[vst], (uint32_t)((2 * g + 1) / NST) & 1u);
         mbar_wait(&p_full[i], pph);
         tc_fence_after();
-        mma_pv_ts<HD>(leader, tmem + kColO + i * 128, tmem + kColS + i * 128, kv_addr(2 * g + 1), j > 0);
+        mma_pv_ts<HD>(leader, tmem + kColO + i * 128, tmem + kColS + i * 128, kv_addr(2 * g + 1), j > 0, sbase + CF::kOffOnes);
         if (j == nkb - 1) commit_if(leader, &o_full[i]);
         if (i == nt - 1) commit_if(leader, &kv_empty[vst]);
         if (g + 1 < total) issue_scores(g + 1, i);
@@ -184,35 +192,36 @@ attn_fa_fwd_kernel(const __grid_constant__ AttnMaps maps, float* __restrict__ ls
       int b, h, qp;
       decode(n, b, h, qp);
       if (i >= nt) break;                           // T = 128: one query tile, the second group has no work
-      float m_used = 0.f, l = 0.f;
+      float m_used = 0.f;
       for (int j = 0; j < nkb; ++j, ++sc) {
         mbar_wait(&s_full[i], (uint32_t)sc & 1u);
         tc_fence_after();
-        // pass 1: row maximum of the block
-        float mx = -INFINITY;
+        // the whole score row of the block -> registers (second pair of loads flies under the first half's maximum)
+        float v[128];
+        tmem_ld32_nowait(tS, v);
+        tmem_ld32_nowait(tS + 32, v + 32);
+        tmem_wait_ld();
+        tmem_ld32_nowait(tS + 64, v + 64);
+        tmem_ld32_nowait(tS + 96, v + 96);
+        float mx = fmaxf(v[0], v[1]);
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          float v[64];
-          tmem_ld32_nowait(tS + half * 64, v);
-          tmem_ld32_nowait(tS + half * 64 + 32, v + 32);
-          tmem_wait_ld();
+        for (int e = 2; e < 64; e += 2) mx = fmaxf(mx, fmaxf(v[e], v[e + 1]));
+        tmem_wait_ld();
 #pragma unroll
-          for (int e = 0; e < 64; e += 2) mx = fmaxf(mx, fmaxf(v[e], v[e + 1]));
-        }
+        for (int e = 64; e < 128; e += 2) mx = fmaxf(mx, fmaxf(v[e], v[e + 1]));
         const float m_blk = mx * scale_log2;
         if (j == 0) {
           m_used = m_blk;
         } else {
           const bool grow = m_blk > m_used + kRescaleThreshold;
           if (__any_sync(0xffffffffu, grow)) {
-            // rare: move this row's reference maximum and rescale its accumulator row in TMEM (PV of block j-1 has
-            // retired: s_full of block j was committed behind it)
+            // rare: move this row's reference maximum and rescale its accumulator row (and its running sum, column
+            // kND) in TMEM.  PV of block j-1 has retired: s_full of block j was committed behind it.
             const float m_new = grow ? m_blk : m_used;
             const float alpha = ex2(m_used - m_new);
             m_used = m_new;
-            l *= alpha;
 #pragma unroll
-            for (int c0 = 0; c0 < TL::kND; c0 += 16) {
+            for (int c0 = 0; c0 < TL::kND + 16; c0 += 16) {
               float x[16];
               tmem_ld16_nowait(tO + c0, x);
               tmem_wait_ld();
@@ -222,25 +231,20 @@ attn_fa_fwd_kernel(const __grid_constant__ AttnMaps maps, float* __restrict__ ls
             }
           }
         }
-        // pass 2: P = 2^(s * scale - m) -> bf16 pairs over the S row (chunk c of P lands on columns already consumed)
-        float la = 0.f, lb = 0.f;
+        // P = 2^(s * scale - m) -> bf16 pairs over the S row.  The row sum is NOT taken here: the PV MMA carries a ones
+        // column (O[:, kND] += P . 1), so the 128 adds per row leave the softmax warps for the tensor pipe.
+        const float neg_m = -m_used;
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-          float v[32];
-          tmem_ld32_nowait(tS + c * 32, v);
-          tmem_wait_ld();
+#pragma unroll
+          for (int e = 0; e < 32; ++e) v[c * 32 + e] = fmaf(v[c * 32 + e], scale_log2, neg_m);
+#pragma unroll
+          for (int e = 0; e < 32; ++e) v[c * 32 + e] = ex2(v[c * 32 + e]);
           uint32_t pk[16];
 #pragma unroll
-          for (int e = 0; e < 32; e += 2) {
-            const float p0 = ex2(fmaf(v[e], scale_log2, -m_used));
-            const float p1 = ex2(fmaf(v[e + 1], scale_log2, -m_used));
-            la += p0;
-            lb += p1;
-            pk[e >> 1] = pack2(p0, p1);
-          }
+          for (int e = 0; e < 32; e += 2) pk[e >> 1] = pack2(v[c * 32 + e], v[c * 32 + e + 1]);
           tmem_st16(tS + c * 16, pk);
         }
-        l += la + lb;
         tmem_wait_st();
         tc_fence_before();
         mbar_arrive(&p_full[i]);
@@ -249,6 +253,13 @@ attn_fa_fwd_kernel(const __grid_constant__ AttnMaps maps, float* __restrict__ ls
       mbar_wait(&o_full[i], (uint32_t)oc & 1u);
       ++oc;
       tc_fence_after();
+      float l;
+      {
+        float x[16];
+        tmem_ld16_nowait(tO + TL::kND, x);          // column kND = sum_k P (the ones column of the PV MMA)
+        tmem_wait_ld();
+        l = x[0];
+      }
       const float inv = 1.f / l;
       const int tok = (2 * qp + i) * kRows + row;
       lse[((int64_t)b * H + h) * T + tok] = (m_used + log2f(l)) * 0.6931471805599453f;

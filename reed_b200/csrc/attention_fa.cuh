@@ -97,18 +97,22 @@ __device__ __forceinline__ void mma_accum(bool leader, uint32_t tmem_d, uint32_t
   }
 }
 // Same product with P in TENSOR MEMORY (64 columns of bf16 pairs at tmem_p, written by the softmax warps)
+// `ones` (optional): a [16 x 16] SWIZZLE_32B tile whose column 0 is 1 -> column kND of D accumulates the row sums of P
 template <int HD>
-__device__ __forceinline__ void mma_pv_ts(bool leader, uint32_t tmem_d, uint32_t tmem_p, uint32_t tile_z, bool accumulate) {
+__device__ __forceinline__ void mma_pv_ts(bool leader, uint32_t tmem_d, uint32_t tmem_p, uint32_t tile_z, bool accumulate,
+                                          uint32_t ones = 0) {
   constexpr uint32_t idesc64 = make_idesc(128, 64, 0, 1);
   constexpr uint32_t idesc16 = make_idesc(128, 16, 0, 1);
   const uint32_t lz = desc_lo(tile_z);
+  const uint64_t d_ones = mk_desc(desc_lo(ones), kHiSw32);
   if (leader) {
 #pragma unroll
     for (int ks = 0; ks < 8; ++ks) {
-      umma_ts(tmem_d, tmem_p + ks * 8, mk_desc(lz + ks * (2048 >> 4), kHiSw128), idesc64, (accumulate || ks > 0) ? 1u : 0u);
+      const uint32_t acc = (accumulate || ks > 0) ? 1u : 0u;
+      umma_ts(tmem_d, tmem_p + ks * 8, mk_desc(lz + ks * (2048 >> 4), kHiSw128), idesc64, acc);
       if (Tile<HD>::kTail)
-        umma_ts(tmem_d + 64, tmem_p + ks * 8, mk_desc(lz + (Tile<HD>::kMain >> 4) + ks * (512 >> 4), kHiSw32), idesc16,
-                (accumulate || ks > 0) ? 1u : 0u);
+        umma_ts(tmem_d + 64, tmem_p + ks * 8, mk_desc(lz + (Tile<HD>::kMain >> 4) + ks * (512 >> 4), kHiSw32), idesc16, acc);
+      if (ones != 0) umma_ts(tmem_d + Tile<HD>::kND, tmem_p + ks * 8, d_ones, idesc16, acc);
     }
   }
 }

@@ -36,6 +36,9 @@ int attn_tc5_bwd(const void* qkv, const void* o, const void* d_o, const float* l
 bool attn_tc5_supported(int T, int hd);
 int attn_fa_fwd(const void* qkv, void* o, float* lse, int B, int T, int H, int hd, cudaStream_t st);
 bool attn_fa_supported(int T, int hd);
+int attn_fa_bwd(const void* qkv, const void* o, const void* d_o, const float* lse, void* dqkv, float* delta, int B, int T,
+                int H, int hd, cudaStream_t st);
+bool attn_fa_bwd_supported(int T, int hd);
 
 }  // namespace reed
 
@@ -163,7 +166,10 @@ extern "C" int reed_attn_bwd(int act_dtype, const void* qkv, const void* o, cons
                              void* dqkv, void* delta, int B, int T, int H, int hd, int backend, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   int which = 0;
-  if (backend == 5) backend = 0;
+  if (backend == 5) {
+    REED_REQUIRE(act_dtype == kBF16 && attn_fa_bwd_supported(T, hd), "attention: fa path required but T=%d hd=%d unsupported", T, hd);
+    return attn_fa_bwd(qkv, o, d_o, (const float*)lse, dqkv, (float*)delta, B, T, H, hd, st);
+  }
   if (attn_pick(act_dtype, T, hd, backend, &which)) return 1;
   if (which == 2) return attn_tc5_bwd(qkv, o, d_o, (const float*)lse, dqkv, (float*)delta, B, T, H, hd, st);
   if (which == 1) return attn_mma_bwd(qkv, o, d_o, (const float*)lse, dqkv, (float*)delta, B, T, H, hd, st);

@@ -7,6 +7,10 @@ namespace reed {
 
 constexpr int UMMA_K = 16;
 
+#ifndef REED_MBAR_SPINS
+#define REED_MBAR_SPINS (1ull << 26)
+#endif
+
 // ------------------------------------------------------------------------------------------------
 // PTX wrappers
 // ------------------------------------------------------------------------------------------------
@@ -34,8 +38,9 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "r"(addr), "r"(parity)
         : "memory");
     if (done) break;
-    if (++spins > (1ull << 26)) {   // ~seconds: a protocol bug must surface as an error, never as a hung GPU
-      printf("reed gemm: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+    if (++spins > REED_MBAR_SPINS) {   // ~seconds: a protocol bug must surface as an error, never as a hung GPU
+      printf("reed: mbarrier wait timed out (block %d thread %d, barrier slot %u, parity %u)\n", blockIdx.x, threadIdx.x,
+             (addr & 1023u) >> 3, parity);
       __trap();
     }
   }
