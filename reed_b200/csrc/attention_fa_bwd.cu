@@ -426,22 +426,28 @@ attn_fa_bwd_kernel(const __grid_constant__ AttnMaps maps, const float* __restric
   if (warp == 13) tmem_dealloc<1>(tmem, 512);
 }
 
-// delta[b, h, t] = sum_d dO[b, t, h, d] * O[b, t, h, d]  (one thread per (token, head); 16-byte loads)
+// delta[b, h, t] = sum_d dO[b, t, h, d] * O[b, t, h, d].  The two tensors are read as one flat stream of 16-byte chunks
+// (consecutive threads = consecutive chunks: fully coalesced); a (token, head) segment is HD / 8 consecutive chunks, whose
+// partial dot products meet in shared memory.
 template <int HD>
-__global__ void attn_delta_kernel(const bf16* __restrict__ o, const bf16* __restrict__ d_o, float* __restrict__ delta, int B,
-                                  int T, int H) {
-  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t total = (int64_t)B * T * H;
-  if (idx >= total) return;
-  const int h = (int)(idx % H);
-  const int64_t tok = idx / H;
-  const uint4* po = reinterpret_cast<const uint4*>(o + idx * HD);
-  const uint4* pd = reinterpret_cast<const uint4*>(d_o + idx * HD);
-  float acc = 0.f;
+__global__ void __launch_bounds__(32 * (HD / 8)) attn_delta_kernel(const uint4* __restrict__ o, const uint4* __restrict__ d_o,
+                                                                   float* __restrict__ delta, int64_t segments, int T, int H) {
+  constexpr int CH = HD / 8;                   // chunks per segment
+  constexpr int SEG = 32;                      // segments per block
+  __shared__ float part[SEG * CH];
+  const int64_t seg0 = (int64_t)blockIdx.x * SEG;
+  const int64_t chunk = seg0 * CH + threadIdx.x;
+  part[threadIdx.x] = chunk < segments * CH ? dot8(o[chunk], d_o[chunk]) : 0.f;
+  __syncthreads();
+  if (threadIdx.x < SEG && seg0 + threadIdx.x < segments) {
+    float acc = 0.f;
 #pragma unroll
-  for (int c = 0; c < HD / 8; ++c) acc += dot8(po[c], pd[c]);
-  const int64_t b = tok / T, t = tok % T;
-  delta[(b * H + h) * T + t] = acc;
+    for (int c = 0; c < CH; ++c) acc += part[threadIdx.x * CH + c];
+    const int64_t idx = seg0 + threadIdx.x;    // = token * H + head
+    const int h = (int)(idx % H);
+    const int64_t tok = idx / H;
+    delta[((tok / T) * H + h) * T + tok % T] = acc;
+  }
 }
 
 template <int HD>
@@ -454,8 +460,9 @@ int bwd_launch(const void* qkv, const void* o, const void* d_o, const float* lse
     done = true;
   }
   {
-    const int64_t total = (int64_t)B * T * H;
-    attn_delta_kernel<HD><<<(unsigned)((total + 255) / 256), 256, 0, st>>>((const bf16*)o, (const bf16*)d_o, delta, B, T, H);
+    const int64_t segments = (int64_t)B * T * H;
+    attn_delta_kernel<HD><<<(unsigned)((segments + 31) / 32), 32 * (HD / 8), 0, st>>>((const uint4*)o, (const uint4*)d_o, delta,
+                                                                                     segments, T, H);
     REED_LAUNCH_CHECK();
   }
   AttnMaps maps;

@@ -30,10 +30,6 @@ int attn_mma_fwd(const void* qkv, void* o, float* lse, int B, int T, int H, int 
 int attn_mma_bwd(const void* qkv, const void* o, const void* d_o, const float* lse, void* dqkv, float* delta, int B,
                  int T, int H, int hd, cudaStream_t st);
 bool attn_mma_supported(int T, int hd);
-int attn_tc5_fwd(const void* qkv, void* o, float* lse, int B, int T, int H, int hd, cudaStream_t st);
-int attn_tc5_bwd(const void* qkv, const void* o, const void* d_o, const float* lse, void* dqkv, float* delta, int B,
-                 int T, int H, int hd, cudaStream_t st);
-bool attn_tc5_supported(int T, int hd);
 int attn_fa_fwd(const void* qkv, void* o, float* lse, int B, int T, int H, int hd, cudaStream_t st);
 bool attn_fa_supported(int T, int hd);
 int attn_fa_bwd(const void* qkv, const void* o, const void* d_o, const float* lse, void* dqkv, float* delta, int B, int T,
@@ -131,17 +127,17 @@ extern "C" int reed_gemm_wgrad_bias(const void* dy, int64_t ld_dy, const void* x
   return reed_colsum(dy, kBF16, ld_dy, db, tokens, n_out, stream);
 }
 
-// backend: 0 auto (tcgen05 kernel when T/hd allow, else mma.sync, else SIMT), 1 force SIMT, 2 require a tensor-core
-// kernel, 3 require the mma.sync kernel, 4 require the tcgen05 kernel
-static int attn_pick(int act_dtype, int T, int hd, int backend, int* which) {
-  const bool tc5_ok = act_dtype == kBF16 && attn_tc5_supported(T, hd);
+// backend: 0 auto (the flash-style tcgen05 kernels when T / head_dim allow, else mma.sync, else SIMT), 1 force SIMT,
+// 2 require a tensor-core kernel, 3 require the mma.sync kernel (ragged / short sequences), 4 or 5 require the tcgen05 kernels
+static int attn_pick(int act_dtype, int T, int hd, int backend, bool fa_ok, int* which) {
+  fa_ok = fa_ok && act_dtype == kBF16;
   const bool mma_ok = act_dtype == kBF16 && attn_mma_supported(T, hd);
-  if (backend == 4) REED_REQUIRE(tc5_ok, "attention: tcgen05 path required but T=%d hd=%d unsupported", T, hd);
+  if (backend == 4 || backend == 5) REED_REQUIRE(fa_ok, "attention: tcgen05 path required but T=%d hd=%d unsupported", T, hd);
   if (backend == 3) REED_REQUIRE(mma_ok, "attention: mma.sync path required but T=%d hd=%d unsupported", T, hd);
-  if (backend == 2) REED_REQUIRE(tc5_ok || mma_ok, "attention: tensor-core path required but T=%d hd=%d unsupported", T, hd);
+  if (backend == 2) REED_REQUIRE(fa_ok || mma_ok, "attention: tensor-core path required but T=%d hd=%d unsupported", T, hd);
   if (backend == 1) *which = 0;
   else if (backend == 3) *which = 1;
-  else if (tc5_ok) *which = 2;
+  else if (fa_ok) *which = 2;
   else if (mma_ok) *which = 1;
   else *which = 0;
   return 0;
@@ -151,12 +147,8 @@ extern "C" int reed_attn_fwd(int act_dtype, const void* qkv, void* o, void* lse,
                              int backend, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   int which = 0;
-  if (backend == 5) {   // the flash-style tcgen05 kernels (round 2), while they are being validated against the round-1 ones
-    REED_REQUIRE(act_dtype == kBF16 && attn_fa_supported(T, hd), "attention: fa path required but T=%d hd=%d unsupported", T, hd);
-    return attn_fa_fwd(qkv, o, (float*)lse, B, T, H, hd, st);
-  }
-  if (attn_pick(act_dtype, T, hd, backend, &which)) return 1;
-  if (which == 2) return attn_tc5_fwd(qkv, o, (float*)lse, B, T, H, hd, st);
+  if (attn_pick(act_dtype, T, hd, backend, attn_fa_supported(T, hd), &which)) return 1;
+  if (which == 2) return attn_fa_fwd(qkv, o, (float*)lse, B, T, H, hd, st);
   if (which == 1) return attn_mma_fwd(qkv, o, (float*)lse, B, T, H, hd, st);
   return attn_simt_fwd(act_dtype, qkv, o, (float*)lse, B, T, H, hd, st);
 }
@@ -166,12 +158,8 @@ extern "C" int reed_attn_bwd(int act_dtype, const void* qkv, const void* o, cons
                              void* dqkv, void* delta, int B, int T, int H, int hd, int backend, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   int which = 0;
-  if (backend == 5) {
-    REED_REQUIRE(act_dtype == kBF16 && attn_fa_bwd_supported(T, hd), "attention: fa path required but T=%d hd=%d unsupported", T, hd);
-    return attn_fa_bwd(qkv, o, d_o, (const float*)lse, dqkv, (float*)delta, B, T, H, hd, st);
-  }
-  if (attn_pick(act_dtype, T, hd, backend, &which)) return 1;
-  if (which == 2) return attn_tc5_bwd(qkv, o, d_o, (const float*)lse, dqkv, (float*)delta, B, T, H, hd, st);
+  if (attn_pick(act_dtype, T, hd, backend, attn_fa_bwd_supported(T, hd), &which)) return 1;
+  if (which == 2) return attn_fa_bwd(qkv, o, d_o, (const float*)lse, dqkv, (float*)delta, B, T, H, hd, st);
   if (which == 1) return attn_mma_bwd(qkv, o, d_o, (const float*)lse, dqkv, (float*)delta, B, T, H, hd, st);
   return attn_simt_bwd(act_dtype, qkv, o, d_o, (const float*)lse, dqkv, (float*)delta, B, T, H, hd, st);
 }
