@@ -26,6 +26,8 @@ import torch
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+TRAFFIC_FILE = "r02_gemm_traffic.json"     # ncu DRAM-traffic capture of the GEMM launches of one xl2 step (profiles/gemm_traffic.py)
+
 CONFIGS = {
     # name: (zoo name, input_size, local batch, z_dims, z_types, enc_depth, enc_depth_text, enc_names, weights, cpu batch)
     "xl2": dict(model="SiT-XL/2", input_size=32, local_batch=32, z_dims=[768], z_types=["i"], encoder_depth=8,
@@ -115,7 +117,9 @@ def run_reference_arm(args, cfg):
         "impl": "reference", "metric": "SiT REED train images/sec", "value": ips, "unit": "images/s",
         "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": per_step * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": cfg["workload"], "cpu_batch": cfg["cpu_batch"]},
+        "config": {"workload": cfg["workload"] + f" - CPU reference arm: the same step at batch {cfg['cpu_batch']} per step "
+                   "(images/s is batch-size independent on the CPU: one image's FLOPs already fill every core)",
+                   "cpu_batch": cfg["cpu_batch"], "gpu_local_batch": cfg["local_batch"]},
         "cpu_baseline": info,
         "e2e": {"value": ips, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -298,20 +302,27 @@ def run_gpu_arm(args, cfg):
     # with CUDA events on the launching stream (an eager step is host-bound, so events around single launches would
     # time Python, not the kernel).  achieved = sum of algorithmic 2*M*N*K / summed launch time.
     roof = None
-    records = []
-    real_gemm = ops.gemm
+    records = []          # (algorithmic flops, replay closure) of every GEMM call that may take the tcgen05 path
+    real_gemm, real_wgrad_bias = ops.gemm, ops.wgrad_bias
 
     def recording(a, b, **kw):
+        before = ops.tcgen05_gemm_launches()
         out = real_gemm(a, b, **kw)
-        M, K = (a.shape[1], a.shape[0]) if kw.get("a_mn") else (a.shape[0], a.shape[1])
-        N = b.shape[1] if kw.get("b_mn") else b.shape[0]
-        tensor_path = (a.dtype == torch.bfloat16 and K >= 64 and N >= 64 and a.stride(0) % 8 == 0 and b.stride(0) % 8 == 0
-                       and not (kw.get("a_mn") and kw.get("b_mn") and K <= 64))
-        if tensor_path:
+        if ops.tcgen05_gemm_launches() > before:          # the library took the tensor-core path for this call
+            M, K = (a.shape[1], a.shape[0]) if kw.get("a_mn") else (a.shape[0], a.shape[1])
+            N = b.shape[1] if kw.get("b_mn") else b.shape[0]
             kw2 = dict(kw)
             kw2["out"] = out
-            records.append((2.0 * M * N * K, a, b, kw2))
+            records.append((2.0 * M * N * K, lambda a=a, b=b, kw2=kw2: real_gemm(a, b, **kw2)))
         return out
+
+    def recording_wgrad_bias(dy2d, x_ext, k_in, dw, db, accumulate):
+        before = ops.tcgen05_gemm_launches()
+        real_wgrad_bias(dy2d, x_ext, k_in, dw, db, accumulate)
+        if ops.tcgen05_gemm_launches() > before:
+            tokens, n_out = dy2d.shape                     # dW[n_out, k_in] and db[n_out]: k_in + 1 useful output columns
+            records.append((2.0 * tokens * n_out * (k_in + 1),
+                            lambda: real_wgrad_bias(dy2d, x_ext, k_in, dw, db, accumulate)))
 
     def eager_step(i):
         x, y, zs = resident[i % n_buf]
@@ -319,25 +330,28 @@ def run_gpu_arm(args, cfg):
 
     if world > 1:
         dist.barrier()
-    ops.gemm = recording
+    ops.gemm, ops.wgrad_bias = recording, recording_wgrad_bias
+    tc_before = ops.tcgen05_gemm_launches()
     try:
         eager_step(0)                      # every rank runs it so the collectives stay matched
         torch.cuda.synchronize()
     finally:
-        ops.gemm = real_gemm
+        ops.gemm, ops.wgrad_bias = real_gemm, real_wgrad_bias
+    tc_launches_in_step = ops.tcgen05_gemm_launches() - tc_before
+    assert len(records) == tc_launches_in_step, (len(records), tc_launches_in_step)   # the sample is the whole population
     if rank == 0 and records:
         reps = 3
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
-            for _, a, b, kw in records[:8]:
-                real_gemm(a, b, **kw)
+            for _, replay in records[:8]:
+                replay()
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph):
-            for _, a, b, kw in records:
-                real_gemm(a, b, **kw)
+            for _, replay in records:
+                replay()
         graph.replay()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -354,16 +368,20 @@ def run_gpu_arm(args, cfg):
         except Exception:
             pass
         peak = peaks.get("bf16_tflops_sustained") or 1400.0
-        traffic = None     # DRAM bytes per GEMM launch, from the committed ncu capture of the same step (xl2 workload only)
+        # DRAM bytes per GEMM launch, from the committed ncu capture of the same step on the same build (xl2 workload only;
+        # profiles/gemm_traffic.py writes it and records the launch count it saw: it must equal launches_timed)
+        traffic, traffic_launches = None, None
         try:
             if args.config == "xl2":
-                traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_gemm_traffic.json")))["dram_bytes_per_launch"]
+                tj = json.load(open(os.path.join(ROOT, "profiles", TRAFFIC_FILE)))
+                traffic, traffic_launches = tj["dram_bytes_per_launch"], tj.get("launches")
         except Exception:
             pass
         achieved = flops / (tms * 1e-3) / 1e12 if tms > 0 else 0.0
         roof = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                "traffic": traffic, "traffic_source": "profiles/r01_gemm_traffic.json (ncu dram bytes, mean per launch)"
-                if traffic is not None else None, "kernel": "gemm_tcgen05_kernel", "launches_timed": len(records),
+                "traffic": traffic, "traffic_source": f"profiles/{TRAFFIC_FILE} (ncu dram bytes, mean per launch over "
+                f"{traffic_launches} launches)" if traffic is not None else None, "kernel": "gemm_tcgen05_kernel",
+                "launches_timed": len(records), "tcgen05_launches_per_step": tc_launches_in_step,
                 "avg_launch_us": tms * 1e3 / len(records),
                 "method": "all tcgen05 GEMM launches of one train step replayed back to back in a CUDA graph, CUDA events",
                 "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)"

@@ -32,6 +32,9 @@ int reed_device_check(char* name, int name_len);
  * sets it around backward so the overlapped NCCL gradient all-reduce (train.py:151,293,401 - accelerate/DDP) finds
  * SMs without splitting a GEMM grid into two waves.  Host-side state, not a stream operation. */
 int reed_gemm_reserve_sms(int n);
+/* Running count of tcgen05 GEMM kernel launches issued through reed_gemm / reed_gemm_wgrad_bias since the library was
+ * loaded (host-side counter; measurement bookkeeping: bench.py's roofline sample must cover every one of a step). */
+int reed_gemm_tcgen05_launches(long long* out);
 
 /* D[M,N] = epilogue(A[M,K] . B[N,K]^T)   -- every nn.Linear of the model and its dgrad/wgrad.
  * Replaces: timm Attention.qkv/.proj and Mlp.fc1/.fc2 (models/sit.py:114-124,134-135), adaLN linears (125-133,

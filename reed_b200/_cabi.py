@@ -18,6 +18,7 @@ P, I, L, F, D = c_void_p, c_int, c_int64, c_float, c_double
 _SIGNATURES = {
     "reed_device_check": [c_char_p, I],
     "reed_gemm_reserve_sms": [I],
+    "reed_gemm_tcgen05_launches": [P],
     "reed_gemm": [I, P, L, I, P, L, I, P, L, I, I, I, I, I, P, P, L, P, L, I, P, L, I, I, P],
     "reed_attn_fwd": [I, P, P, P, I, I, I, I, I, P],
     "reed_attn_bwd": [I, P, P, P, P, P, P, I, I, I, I, I, P],

@@ -58,6 +58,15 @@ extern "C" int reed_device_check(char* name, int name_len) {
 // SMs the persistent tensor-core GEMM grids leave free from now on (host-side planner state; 0 = use every SM).
 // The data-parallel trainer raises it around backward so the NCCL all-reduce kernels of finished gradient buckets
 // find SMs without pushing part of a GEMM grid into a second wave (train.py:401: DDP's overlapped all-reduce).
+// Running count of tcgen05 GEMM kernel launches made through reed_gemm / reed_gemm_wgrad_bias (host-side bookkeeping):
+// bench.py checks that the launches it times for the roofline are ALL the tensor-core GEMM launches of a step.
+static long long g_tcgen05_launches = 0;
+extern "C" int reed_gemm_tcgen05_launches(long long* out) {
+  REED_REQUIRE(out != nullptr, "gemm_tcgen05_launches: null output");
+  *out = g_tcgen05_launches;
+  return 0;
+}
+
 extern "C" int reed_gemm_reserve_sms(int n) {
   REED_REQUIRE(n >= 0 && n <= 64, "gemm_reserve_sms: %d out of range", n);
   gemm_tcgen05_reserve_sms(n);
@@ -95,6 +104,7 @@ extern "C" int reed_gemm(int act_dtype, const void* A, int64_t lda, int a_mn_maj
   if (backend != 1 && tc_ok && !tiny_wgrad) {
     gemm_tcgen05_force_cta_group(backend == 3 ? 1 : (backend == 4 ? 2 : 0));
     gemm_tcgen05_force_bn(force_bn == 1 ? 128 : (force_bn == 2 ? 192 : (force_bn == 3 ? 256 : 0)));
+    ++g_tcgen05_launches;
     return gemm_tcgen05(A, lda, a_mn_major, B, ldb, b_mn_major, D, ldd, d_dtype, M, N, K, ep, st);
   }
   return gemm_simt(act_dtype, A, lda, a_mn_major, B, ldb, b_mn_major, D, ldd, d_dtype, M, N, K, ep, st);
@@ -120,6 +130,7 @@ extern "C" int reed_gemm_wgrad_bias(const void* dy, int64_t ld_dy, const void* x
   if (tokens > 64 && gemm_tcgen05_supported(ld_dy, ld_x, ldd, dy, x_ext, n_out, N, tokens)) {
     gemm_tcgen05_force_cta_group(0);
     gemm_tcgen05_force_bn(0);
+    ++g_tcgen05_launches;
     return gemm_tcgen05(dy, ld_dy, 1, x_ext, ld_x, 1, dW, ldd, kF32, n_out, N, tokens, ep, st);
   }
   ep.bias_grad = nullptr; ep.n_store = 0;

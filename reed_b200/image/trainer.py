@@ -39,7 +39,6 @@ class Bucket:
         self.work = None
         self.sharded = False       # optimizer state of this bucket is partitioned across the data-parallel ranks
         self.gather_work = None    # in-flight all-gather of the bf16 shadows / fp32 masters (sharded optimizer)
-        self.norm_done = False     # REED_EARLY_NORM: this step's sum of squares was already taken after the block's backward
 
     def shard(self, rank: int, world: int):
         """(first element, element count) of the slice rank ``rank`` owns; the whole bucket when it is not sharded."""
@@ -156,7 +155,6 @@ class FlatState:
         gradients that arrive through autograd (the label-embedding table) are zeroed and accumulated into."""
         for b in self.buckets:
             b.work = None
-            b.norm_done = False
             b.zero_group.zeroed = False
             for p, off in zip(b.params, b.offsets):
                 if p._reed_kernel_grad:
@@ -290,10 +288,6 @@ class ReedTrainer:
         self._state_complete = True          # ... and of the masters / EMA / moments (gather_state() completes them)
         self._step_dev = torch.zeros(1, device=dev, dtype=torch.int32)   # device copy of step_count (graph replays)
         self._graph = None
-        # REED_EARLY_NORM=1 (experiment, single GPU only): sum the squares of a block's gradients right after that block's
-        # backward, while the 96 MB the weight-gradient GEMMs just wrote are still largely in the 126 MB L2, instead of
-        # re-reading all 2.7 GB from HBM in the optimizer tail
-        self._early_norm = os.environ.get("REED_EARLY_NORM", "0") == "1" and self.reducer.world == 1
         # all-reduce each block's bucket as soon as that block's backward has produced its last gradient
         for i, blk in enumerate(model.blocks):
             bucket = self.state.bucket_of_block(i)
@@ -303,16 +297,11 @@ class ReedTrainer:
 
     def _begin_step(self):
         self.state.begin_step()
-        if self._early_norm:
-            self._norm_sq.zero_()
         if self.nvls is not None:            # the multicast reduce-scatter kernels add their slices' squares during backward
             self._norm_sq_shard.zero_()
 
     def _after_block_backward(self, bucket: Bucket):
         self.reducer.launch(bucket)
-        if self._early_norm and self.reducer.enabled and not bucket.norm_done:
-            ops._launch("reed_grad_sumsq", bucket.grad.data_ptr(), bucket.numel, self._norm_sq.data_ptr(), ops._stream())
-            bucket.norm_done = True
 
     def compute_loss(self, images, labels, zs, diffusion_decay=1.0, repa_decay=1.0, time_input=None):
         """diffusion_decay / repa_decay: Python floats or 0-d device tensors (the curriculum scalars of train.py:363-385)."""
@@ -330,11 +319,9 @@ class ReedTrainer:
         self.step_count += 1
         self._step_dev += 1
         st = ops._stream()
-        if not self._early_norm:
-            self._norm_sq.zero_()
+        self._norm_sq.zero_()
         for b in self.state.buckets:
-            if not b.norm_done:
-                ops._launch("reed_grad_sumsq", b.grad.data_ptr(), b.numel, self._norm_sq.data_ptr(), st)
+            ops._launch("reed_grad_sumsq", b.grad.data_ptr(), b.numel, self._norm_sq.data_ptr(), st)
         clip = self.max_grad_norm is not None and self.max_grad_norm > 0
         for b in self.state.buckets:
             ops._launch("reed_adamw_ema", b.param.data_ptr(), b.grad.data_ptr(), b.exp_avg.data_ptr(),

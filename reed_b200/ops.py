@@ -26,10 +26,11 @@ import os as _os
 
 # profiling knob: 0 = bias gradients of qkv / fc1 by a separate column-sum pass instead of the ones-column GEMM
 _WGRAD_BIAS = _os.environ.get("REED_WGRAD_BIAS", "1") != "0"
-# experiment (off by default, not yet run on hardware): weight-gradient GEMMs of a transformer block go to a second stream.
-# They depend only on dy and the saved activations, not on the dgrad chain, so their CTAs can fill the SMs a dgrad GEMM
-# leaves idle in its last partial round (N = 1152 shapes run 160 tiles on 74 CTA pairs: the third round is 16 % full)
-_WGRAD_STREAM = _os.environ.get("REED_WGRAD_STREAM", "0") == "1"
+# Weight-gradient GEMMs of a transformer block go to a second stream (trainer mode).  They depend only on dy and the saved
+# activations, not on the dgrad chain, so their CTAs fill the SMs a dgrad GEMM leaves idle in its last partial round
+# (N = 1152 shapes run 160 tiles on 74 CTA pairs: the third round is 16 % full).  Measured on the B200 in round 2:
+# 909 -> 927 img/s on the XL/2 step (profiles/r02_bench_flags.txt); REED_WGRAD_STREAM=0 restores the single stream for A/B.
+_WGRAD_STREAM = _os.environ.get("REED_WGRAD_STREAM", "1") != "0"
 _gemm_backend = BACKEND_AUTO
 _attn_backend = BACKEND_AUTO
 launch_count = 0     # kernels launched through this module (bench.py reports it as gpu_launches)
@@ -476,31 +477,20 @@ class TokenMeanFn(torch.autograd.Function):
         return dx, None
 
 
-class LNModulateFn(torch.autograd.Function):
-    """modulate(LayerNorm(x), shift, scale) with x [B,T,D] fp32, shift/scale [B,D] fp32 views (sit.py:26-27,153-155)."""
+def _lib():
+    """torch.ops.reed namespace (reed_b200.library registers the custom ops on first use)."""
+    from . import library  # noqa: F401
+    return torch.ops.reed
+
+
+class LNModulateFn:
+    """modulate(LayerNorm(x), shift, scale) with x [B,T,D] fp32, shift/scale [B,D] fp32 views (sit.py:26-27,153-155):
+    the differentiable custom op ``reed::ln_modulate`` (kept under the round-1 name for its callers)."""
 
     @staticmethod
-    def forward(ctx, x, shift, scale, act_dtype):
+    def apply(x, shift, scale, act_dtype):
         _require_cuda(x)
-        B, T, D = x.shape
-        x2 = x.contiguous().view(B * T, D)
-        if shift.stride(0) != scale.stride(0) or shift.stride(1) != 1 or scale.stride(1) != 1:
-            shift, scale = shift.contiguous(), scale.contiguous()
-        out, mean, rstd = ln_modulate_fwd(x2, shift, scale, T, act_dtype)
-        ctx.save_for_backward(x2, mean, rstd, scale)
-        ctx.dims = (B, T, D)
-        return out.view(B, T, D)
-
-    @staticmethod
-    def backward(ctx, dout):
-        x2, mean, rstd, scale = ctx.saved_tensors
-        B, T, D = ctx.dims
-        ld = scale.stride(0)
-        # gradient buffers laid out with the same row stride as the (possibly strided) scale view
-        buf = torch.zeros((2, B, ld), device=x2.device, dtype=torch.float32)
-        dshift, dscale = buf[0][:, :D], buf[1][:, :D]
-        dx = ln_modulate_bwd(dout.contiguous().view(B * T, D), x2, mean, rstd, scale, T, None, dshift, dscale)
-        return dx.view(B, T, D), dshift, dscale, None
+        return _lib().ln_modulate(x, shift, scale, act_dtype == torch.bfloat16)[0]
 
 
 class SiTBlockFn(torch.autograd.Function):
@@ -636,9 +626,7 @@ class SiTBlockFn(torch.autograd.Function):
 # SILoss pieces (loss.py:175-186, 204-225)
 # --------------------------------------------------------------------------------------------------
 
-def interpolate(x, eps, t, path_type):
-    """x_t = alpha_t x + sigma_t eps with per-sample t (no autograd: inputs are data)."""
-    _require_cuda(x, eps, t)
+def _interpolate_raw(x, eps, t, path_type):
     x, eps = x.contiguous(), eps.contiguous()
     out = torch.empty_like(x)
     B = x.shape[0]
@@ -646,54 +634,64 @@ def interpolate(x, eps, t, path_type):
     return out
 
 
-class VelocityMSEFn(torch.autograd.Function):
-    """mean_flat((pred - (dalpha x + dsigma eps))^2) -> (B,)"""
+def interpolate(x, eps, t, path_type):
+    """x_t = alpha_t x + sigma_t eps with per-sample t (no autograd: inputs are data); custom op ``reed::siloss_interp``."""
+    _require_cuda(x, eps, t)
+    return _lib().siloss_interp(x, eps, t, path_type)
+
+
+def _mse_fwd_raw(pred, x, eps, t, path_type):
+    pred = pred.contiguous()
+    B = pred.shape[0]
+    out = torch.empty((B,), device=pred.device, dtype=torch.float32)
+    _launch("reed_siloss_mse_fwd", _p(pred), _p(x), _p(eps), _p(t), _p(out), B, pred.numel() // B, path_type, _stream())
+    return out
+
+
+def _mse_bwd_raw(pred, x, eps, t, g, path_type):
+    pred = pred.contiguous()
+    B = pred.shape[0]
+    g = g.contiguous().float()
+    dpred = torch.empty_like(pred)
+    _launch("reed_siloss_mse_bwd", _p(pred), _p(x), _p(eps), _p(t), _p(g), _p(dpred), B, pred.numel() // B, path_type, _stream())
+    return dpred
+
+
+class VelocityMSEFn:
+    """mean_flat((pred - (dalpha x + dsigma eps))^2) -> (B,): the differentiable custom op ``reed::velocity_mse``."""
 
     @staticmethod
-    def forward(ctx, pred, x, eps, t, path_type):
+    def apply(pred, x, eps, t, path_type):
         _require_cuda(pred, x, eps, t)
-        pred = pred.contiguous()
-        B = pred.shape[0]
-        out = torch.empty((B,), device=pred.device, dtype=torch.float32)
-        _launch("reed_siloss_mse_fwd", _p(pred), _p(x), _p(eps), _p(t), _p(out), B, pred.numel() // B, path_type, _stream())
-        ctx.save_for_backward(pred, x, eps, t)
-        ctx.path_type = path_type
-        return out
+        return _lib().velocity_mse(pred, x.contiguous(), eps.contiguous(), t, path_type)
+
+
+def _cos_fwd_raw(zt, z):
+    zt, z = zt.contiguous(), z.contiguous()
+    B, T, Z = zt.shape
+    stats = torch.empty((B * T, 3), device=zt.device, dtype=torch.float32)
+    align = torch.zeros((B,), device=zt.device, dtype=torch.float32)
+    _launch("reed_siloss_cos_fwd", _p(zt), _code(zt.dtype), _p(z), _code(z.dtype), _p(stats), _p(align), B, T, Z, _stream())
+    return align, stats
+
+
+def _cos_bwd_raw(zt, z, stats, g):
+    zt, z = zt.contiguous(), z.contiguous()
+    B, T, Z = zt.shape
+    g = g.contiguous().float()
+    dzt = torch.empty_like(zt)
+    _launch("reed_siloss_cos_bwd", _p(zt), _code(zt.dtype), _p(z), _code(z.dtype), _p(stats), _p(g), _p(dzt), B, T, Z, _stream())
+    return dzt
+
+
+class CosineAlignFn:
+    """-(normalize(z) . normalize(z~)).sum(-1).mean(-1) -> (B,);  z~: [B,T,Z] (grad), z: [B,T,Z] target: the differentiable
+    custom op ``reed::cosine_align``."""
 
     @staticmethod
-    def backward(ctx, g):
-        pred, x, eps, t = ctx.saved_tensors
-        B = pred.shape[0]
-        g = g.contiguous().float()
-        dpred = torch.empty_like(pred)
-        _launch("reed_siloss_mse_bwd", _p(pred), _p(x), _p(eps), _p(t), _p(g), _p(dpred), B, pred.numel() // B,
-                ctx.path_type, _stream())
-        return dpred, None, None, None, None
-
-
-class CosineAlignFn(torch.autograd.Function):
-    """-(normalize(z) . normalize(z~)).sum(-1).mean(-1) -> (B,);  z~: [B,T,Z] (grad), z: [B,T,Z] target."""
-
-    @staticmethod
-    def forward(ctx, zt, z):
+    def apply(zt, z):
         _require_cuda(zt, z)
-        zt, z = zt.contiguous(), z.contiguous()
-        B, T, Z = zt.shape
-        stats = torch.empty((B * T, 3), device=zt.device, dtype=torch.float32)
-        align = torch.zeros((B,), device=zt.device, dtype=torch.float32)
-        _launch("reed_siloss_cos_fwd", _p(zt), _code(zt.dtype), _p(z), _code(z.dtype), _p(stats), _p(align), B, T, Z, _stream())
-        ctx.save_for_backward(zt, z, stats)
-        return align
-
-    @staticmethod
-    def backward(ctx, g):
-        zt, z, stats = ctx.saved_tensors
-        B, T, Z = zt.shape
-        g = g.contiguous().float()
-        dzt = torch.empty_like(zt)
-        _launch("reed_siloss_cos_bwd", _p(zt), _code(zt.dtype), _p(z), _code(z.dtype), _p(stats), _p(g), _p(dzt), B, T, Z,
-                _stream())
-        return dzt, None
+        return _lib().cosine_align(zt, z)[0]
 
 
 # --------------------------------------------------------------------------------------------------
@@ -724,6 +722,14 @@ def sampler_step(x_cur, v, *, eps=None, d_prev=None, want_slope=False, next_dup=
     _launch("reed_sampler_step", _p(x_cur), _p(v), _code(v.dtype), _p(eps), _p(d_prev), _p(slope), _p(x_next), _p(x_model),
             n, int(guided), int(bool(next_dup)), int(sde), path_type, float(cfg), float(t_cur), float(dt), _stream())
     return x_next, slope, x_model
+
+
+def tcgen05_gemm_launches() -> int:
+    """Running count of tcgen05 GEMM kernel launches made by the library (reed_gemm and reed_gemm_wgrad_bias)."""
+    import ctypes
+    n = ctypes.c_longlong(0)
+    call("reed_gemm_tcgen05_launches", ctypes.byref(n))
+    return int(n.value)
 
 
 def device_check():

@@ -210,3 +210,23 @@ def test_preprocess_plan_matches_reference_substring_rules():
     assert _plan("dinov2-vit-b", 512)[2] == 448 and _plan("sam", 256) is None
     x = torch.zeros(1, 3, 8, 8)
     assert preprocess_raw_image(x, "sam") is x
+
+
+def test_custom_ops_are_registered_with_fake_kernels():
+    """torch.ops.reed.* exist, carry schemas, and their fake kernels give the output shapes/dtypes without a device run."""
+    from torch._subclasses.fake_tensor import FakeTensorMode
+    from reed_b200 import library
+    for name in library.OPS:
+        op = getattr(torch.ops.reed, name)
+        assert str(op.default._schema).startswith(f"reed::{name}(")
+    with FakeTensorMode():
+        x, s = torch.empty(2, 16, 32, device="cuda"), torch.empty(2, 32, device="cuda")
+        out, mean, rstd = torch.ops.reed.ln_modulate(x, s, s, True)
+        assert out.shape == (2, 16, 32) and out.dtype == torch.bfloat16 and mean.shape == rstd.shape == (32,)
+        qkv = torch.empty(2 * 256, 3 * 2 * 72, device="cuda", dtype=torch.bfloat16)
+        o, lse = torch.ops.reed.attention(qkv, 2, 256, 2, 72)
+        assert o.shape == (512, 144) and lse.shape == (2, 2, 256) and lse.dtype == torch.float32
+        y, h = torch.ops.reed.linear(torch.empty(8, 64, device="cuda"), torch.empty(16, 64, device="cuda"), None, 2, False)
+        assert y.shape == h.shape == (8, 16)
+        assert torch.ops.reed.velocity_mse(torch.empty(3, 4, 8, 8, device="cuda"), torch.empty(3, 4, 8, 8, device="cuda"),
+                                           torch.empty(3, 4, 8, 8, device="cuda"), torch.empty(3, device="cuda"), 0).shape == (3,)
