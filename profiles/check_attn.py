@@ -34,6 +34,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--bwd", action="store_true")
     ap.add_argument("--time", action="store_true")
+    ap.add_argument("--no-flush", action="store_true", help="time with a warm L2 (no 256 MB flush between launches)")
     args = ap.parse_args()
     _cabi.load()
     dev = "cuda"
@@ -88,7 +89,8 @@ def main():
                         fn()
                     ts = []
                     for _ in range(15):
-                        flush.sum()
+                        if not args.no_flush:
+                            flush.sum()
                         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                         s.record()
                         fn()

@@ -142,6 +142,16 @@ __device__ __forceinline__ void load_tile(const CUtensorMap* main, const CUtenso
   tma_load_3d(main, bar, dst, 0, hcol, row0);
   if (Tile<HD>::kTail) tma_load_3d(tail, bar, dst + Tile<HD>::kMain, 64, hcol, row0);
 }
+// pull the same tile into L2 only (no shared memory, no barrier): issued a step ahead of the load that needs it
+__device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap* map, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(map), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+template <int HD>
+__device__ __forceinline__ void prefetch_tile(const CUtensorMap* main, const CUtensorMap* tail, int hcol, int row0) {
+  tma_prefetch_3d(main, 0, hcol, row0);
+  if (Tile<HD>::kTail) tma_prefetch_3d(tail, 64, hcol, row0);
+}
 // store a staged [128 x hd] tile (main SWIZZLE_128B at `src`, 8-column tail rows of 16 B at src + kMain)
 template <int HD>
 __device__ __forceinline__ void store_tile(const CUtensorMap* main, const CUtensorMap* tail8, uint32_t src, int hcol, int row0) {

@@ -139,10 +139,11 @@ def _(x, shift, scale, bf16):
 def ln_modulate_bwd(dout: Tensor, x: Tensor, mean: Tensor, rstd: Tensor, scale: Tensor) -> Tuple[Tensor, Tensor, Tensor]:
     B, T, D = x.shape
     scale = scale.contiguous()
-    grads = torch.zeros((2, B, D), device=x.device, dtype=torch.float32)
+    dshift = torch.zeros((B, D), device=x.device, dtype=torch.float32)     # separate storages: op outputs may not alias
+    dscale = torch.zeros((B, D), device=x.device, dtype=torch.float32)
     dx = ops.ln_modulate_bwd(dout.contiguous().view(B * T, D), x.contiguous().view(B * T, D), mean, rstd, scale, T, None,
-                             grads[0], grads[1])
-    return dx.view(B, T, D), grads[0], grads[1]
+                             dshift, dscale)
+    return dx.view(B, T, D), dshift, dscale
 
 
 @ln_modulate_bwd.register_fake
