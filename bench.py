@@ -179,11 +179,13 @@ def build_trainer(cfg, dev, precision="bf16"):
                 p.copy_(torch.randn(p.shape, generator=g) * 0.02)
     model = model.to(dev).train()
     loss_fn = SILoss(enc_names=cfg["enc_names"], loss_weights=cfg["loss_weights"])
-    # REED_SHARD_OPT=1: sharded optimizer (reduce-scatter + slice-wise clip/AdamW/EMA + operand all-gather); off by default
-    # until it has been validated on GPUs (profiles/check_sharded.py)
+    # With more than one rank the trainer shards the optimizer and exchanges gradients / operands with its own NVSwitch
+    # multicast kernels (profiles/r02_sharded_check.txt).  A/B knobs: REED_NVLS=0 -> NCCL reduce-scatter / all-gather,
+    # REED_SHARD_OPT=0 -> replicated optimizer behind an NCCL all-reduce (round 1's data path).
+    shard = os.environ.get("REED_SHARD_OPT", "1") != "0"
     return ReedTrainer(model, loss_fn, precision=precision, comm_sms=int(os.environ.get("REED_COMM_SMS", "16")),
-                       shard_optimizer=os.environ.get("REED_SHARD_OPT", "0") == "1" or os.environ.get("REED_NVLS", "0") == "1",
-                       nvls=os.environ.get("REED_NVLS", "0") == "1"), spec
+                       shard_optimizer=shard if shard is False else None,
+                       nvls=False if (not shard or os.environ.get("REED_NVLS", "1") == "0") else None), spec
 
 
 def make_batches(cfg, spec, dev, n_buf):

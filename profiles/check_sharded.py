@@ -1,4 +1,4 @@
-"""Round-2 check of the sharded optimizer on real kernels (never run on GPUs yet - written after round 1's GPU minutes):
+"""Check of the sharded optimizer on real kernels (run on 2 x B200 in round 2: profiles/r02_sharded_check.txt):
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 \
         profiles/check_sharded.py [--graphed] [--nvls]
@@ -68,13 +68,18 @@ def main():
                     named[f"{name}/{field}"] = getattr(b, field)[off:off + p.numel()].float().clone()
         results.append((losses, named, float(tr.grad_norm())))
     (l0, n0, g0), (l1, n1, g1) = results
-    worst = max((float((n0[k] - n1[k]).abs().max()), k) for k in n0)
-    ok = all(abs(a - b) <= 1e-4 * max(1.0, abs(a)) for a, b in zip(l0, l1)) and worst[0] <= 5e-4 \
+    # fp32 buffers: absolute 5e-4 (Adam turns last-bit gradient noise - atomics ordering differs between a graph replay and
+    # eager launches - into steps of up to lr = 1e-4); bf16 shadows: one bf16 ulp of the value on top of that
+    def excess(k):
+        tol = 5e-4 + (n0[k].abs() * 2.0 ** -7 if k.endswith("/shadow") else 0.0)
+        return float(((n0[k] - n1[k]).abs() - tol).max())
+    worst = max((excess(k), k) for k in n0)
+    ok = all(abs(a - b) <= 1e-4 * max(1.0, abs(a)) for a, b in zip(l0, l1)) and worst[0] <= 0.0 \
         and abs(g0 - g1) <= 1e-3 * max(1.0, g0)
     flag = torch.tensor([int(ok)], device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:
-        print(f"losses replicated {l0}\nlosses sharded    {l1}\ngrad norm {g0} vs {g1}\nworst buffer diff {worst}")
+        print(f"losses replicated {l0}\nlosses sharded    {l1}\ngrad norm {g0} vs {g1}\nworst excess over tolerance {worst}")
         print("SHARDED OPTIMIZER", "OK" if int(flag) else "MISMATCH")
     dist.barrier()
     dist.destroy_process_group()

@@ -427,7 +427,7 @@ __global__ void __launch_bounds__(256) colsum_kernel(const TA* __restrict__ src,
 // ---------------------------------------------------------------------------------------------
 // flat elementwise: casts, SiLU fwd/bwd, act-derivative multiply
 // ---------------------------------------------------------------------------------------------
-enum UnaryOp { kCast = 0, kSilu = 1 };
+enum UnaryOp { kCast = 0, kSilu = 1, kGeluErf = 2 };   // kGeluErf: nn.GELU() exact, the DINOv2 target encoders' MLP
 
 template <typename TI, typename TO, int OP>
 __global__ void __launch_bounds__(256) unary_kernel(const TI* __restrict__ in, TO* __restrict__ out, int64_t n4) {
@@ -437,6 +437,10 @@ __global__ void __launch_bounds__(256) unary_kernel(const TI* __restrict__ in, T
     if (OP == kSilu) {
 #pragma unroll
       for (int j = 0; j < 4; ++j) v.v[j] = silu(v.v[j]);
+    }
+    if (OP == kGeluErf) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) v.v[j] = 0.5f * v.v[j] * (1.f + erff(v.v[j] * 0.70710678118654752f));
     }
     store4(out + i * 4, v);
   }
@@ -795,18 +799,22 @@ extern "C" int reed_colsum(const void* src, int act_dtype, int64_t ld, void* out
   return 0;
 }
 
-// op: 0 cast, 1 silu.  in_dtype/out_dtype: 0 fp32, 1 bf16 (fp32->fp32, fp32->bf16, bf16->fp32 supported)
+// op: 0 cast, 1 silu, 2 gelu (erf).  in_dtype/out_dtype: 0 fp32, 1 bf16
 extern "C" int reed_unary(const void* in, int in_dtype, void* out, int out_dtype, int op, int64_t n, void* stream) {
   REED_REQUIRE(n % 4 == 0, "unary needs n %% 4 == 0, got %lld", (long long)n);
   if (n == 0) return 0;
   int64_t n4 = n / 4;
   int grid = flat_grid(n4);
   cudaStream_t st = (cudaStream_t)stream;
+  REED_REQUIRE(op >= kCast && op <= kGeluErf, "reed_unary: unknown op %d", op);
 #define UN(TI, TO, OP) unary_kernel<TI, TO, OP><<<grid, 256, 0, st>>>((const TI*)in, (TO*)out, n4)
-  if (in_dtype == kF32 && out_dtype == kF32) { if (op == kSilu) UN(float, float, kSilu); else UN(float, float, kCast); }
-  else if (in_dtype == kF32 && out_dtype == kBF16) { if (op == kSilu) UN(float, bf16, kSilu); else UN(float, bf16, kCast); }
-  else if (in_dtype == kBF16 && out_dtype == kF32) { if (op == kSilu) UN(bf16, float, kSilu); else UN(bf16, float, kCast); }
+#define UN3(TI, TO) do { if (op == kSilu) UN(TI, TO, kSilu); else if (op == kGeluErf) UN(TI, TO, kGeluErf); else UN(TI, TO, kCast); } while (0)
+  if (in_dtype == kF32 && out_dtype == kF32) UN3(float, float);
+  else if (in_dtype == kF32 && out_dtype == kBF16) UN3(float, bf16);
+  else if (in_dtype == kBF16 && out_dtype == kF32) UN3(bf16, float);
+  else if (in_dtype == kBF16 && out_dtype == kBF16) UN3(bf16, bf16);
   else return fail("reed_unary: unsupported dtype pair %d -> %d", in_dtype, out_dtype);
+#undef UN3
 #undef UN
   REED_LAUNCH_CHECK();
   return 0;

@@ -16,7 +16,7 @@
 //
 // Ordering is the caller's job (nvls.py): a cross-rank barrier on the stream before the reduce-scatter (all ranks have
 // finished writing the bucket's gradients) and before the next forward (all ranks' multicast operand stores are done).
-// NOT YET RUN ON HARDWARE: written after round 1's GPU minutes were spent; off unless REED_NVLS=1.
+// Validated on 2 x B200 in round 2 (profiles/r02_sharded_check.txt); the trainer's default exchange for world > 1.
 #include <math.h>
 #include "common.cuh"
 

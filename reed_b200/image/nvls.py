@@ -1,7 +1,8 @@
 """Host side of the NVSwitch-multicast gradient exchange (csrc/nvls.cu) for the sharded optimizer.
 
-NOT YET RUN ON HARDWARE - written after round 1's GPU minutes were spent; enabled only by ``REED_NVLS=1`` /
-``ReedTrainer(shard_optimizer=True, nvls=True)`` on an NCCL group whose GPUs share an NVSwitch multicast domain.
+Default data path of ``ReedTrainer`` on more than one rank (bf16 mode, NCCL group whose GPUs share an NVSwitch multicast
+domain); validated on 2 x B200 in round 2 against the replicated trainer (profiles/r02_sharded_check.txt).
+``ReedTrainer(nvls=False)`` / ``REED_NVLS=0`` keeps NCCL collectives for the same sharded step.
 
 What it replaces: in the sharded data-parallel step (trainer.py) the NCCL reduce-scatter of every block bucket, the
 per-slice sum-of-squares pass and the NCCL all-gather of the bf16 GEMM operands (train.py:151,293,401 DDP all-reduce ->
@@ -75,7 +76,7 @@ class NvlsExchange:
             hs = self.symm.rendezvous(b.shadow, self.group)
             if not hg.multicast_ptr or not hs.multicast_ptr:
                 raise RuntimeError("NVLS multicast is not available for this process group (needs NVSwitch + fabric "
-                                   "multicast support); run without REED_NVLS")
+                                   "multicast support); construct the trainer with nvls=False (REED_NVLS=0) to use NCCL")
             b.grad_mc, b.shadow_mc = int(hg.multicast_ptr), int(hs.multicast_ptr)
             self.handles[b.name] = (hg, hs)
         torch.cuda.synchronize(dev)

@@ -239,7 +239,7 @@ class ReedTrainer:
 
     def __init__(self, model: nn.Module, loss_fn, *, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0,
                  max_grad_norm=1.0, ema_decay=0.9999, proj_coeff=0.5, precision: Optional[str] = "bf16", group=None,
-                 with_ema=True, comm_sms: int = 16, shard_optimizer: bool = False, nvls: bool = False):
+                 with_ema=True, comm_sms: int = 16, shard_optimizer: Optional[bool] = None, nvls: Optional[bool] = None):
         self.model = model
         self.loss_fn = loss_fn
         self.lr, self.betas, self.eps, self.weight_decay = lr, betas, eps, weight_decay
@@ -252,11 +252,17 @@ class ReedTrainer:
             for p in self.ema.parameters():
                 p.requires_grad_(False)
             self.ema.eval()
-        # Sharded optimizer (ZeRO-1 over NVSwitch; off by default): the clip/AdamW/EMA pass is HBM-bound at 38 B/param and
-        # every rank repeats it on identical data.  With shard_optimizer each rank reduce-scatters the block buckets,
-        # updates 1/world of every block's weights (masters, moments, EMA) and all-gathers only the bf16 GEMM operands
-        # - under the next forward, block by block.  Same arithmetic on every element; see _optimizer_step_sharded.
+        # Sharded optimizer (ZeRO-1 over NVSwitch; the default when there is more than one rank): the clip/AdamW/EMA pass is
+        # HBM-bound at 38 B/param and every rank would repeat it on identical data.  Each rank reduce-scatters the block
+        # buckets, updates 1/world of every block's weights (masters, moments, EMA) and only the bf16 GEMM operands are
+        # gathered - under the next forward, block by block.  Same arithmetic on every element (_optimizer_step_sharded);
+        # validated against the replicated trainer on 2 x B200 (profiles/r02_sharded_check.txt: 1790 -> 1841 img/s, and
+        # 1866 img/s with the multicast kernels below).
         world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+        if shard_optimizer is None:
+            shard_optimizer = world > 1
+        if nvls is None:                       # our own multicast kernels need bf16 operands and an NCCL (NVSwitch) group
+            nvls = bool(shard_optimizer) and world > 1 and precision == "bf16" and dist.get_backend(group) == "nccl"
         self.shard = bool(shard_optimizer) and world > 1
         self.precision = precision
         # nvls (needs shard_optimizer, bf16 operands, NCCL group on one NVSwitch domain): the reduce-scatter and the

@@ -76,7 +76,7 @@ def _launch(name, *args, n=1):
 # --------------------------------------------------------------------------------------------------
 
 def cast(x: torch.Tensor, dtype: torch.dtype, op: int = 0) -> torch.Tensor:
-    """dtype cast (op=0) or SiLU+cast (op=1) through reed_unary."""
+    """dtype cast (op=0), SiLU+cast (op=1) or exact erf-GELU+cast (op=2) through reed_unary."""
     if op == 0 and x.dtype == dtype:
         return x
     x = x.contiguous()

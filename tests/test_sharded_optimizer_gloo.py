@@ -109,7 +109,7 @@ def _worker(rank, world, port, out):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         from reed_b200.image.trainer import ReedTrainer
-        rep = ReedTrainer(_tiny_model(), None, precision="bf16")
+        rep = ReedTrainer(_tiny_model(), None, precision="bf16", shard_optimizer=False)
         shd = ReedTrainer(_tiny_model(), None, precision="bf16", shard_optimizer=True)
         for tr in (rep, shd):
             _emulate_kernels(tr)
@@ -160,7 +160,7 @@ def _worker(rank, world, port, out):
                 want, got = _by_name(rep, field), _by_name(shd, field)
                 ok &= all(torch.equal(want[k], got[k]) for k in want)
         # the multicast-exchange wiring (norm partials from the reduce-scatter, one barrier instead of all-gathers)
-        rep2 = ReedTrainer(_tiny_model(), None, precision="bf16")
+        rep2 = ReedTrainer(_tiny_model(), None, precision="bf16", shard_optimizer=False)
         mc = ReedTrainer(_tiny_model(), None, precision="bf16", shard_optimizer=True)
         for tr in (rep2, mc):
             _emulate_kernels(tr)
@@ -188,6 +188,9 @@ def _worker(rank, world, port, out):
             ok &= all(torch.equal(want[k], got[k]) for k in want)
         ck = shd.checkpoint()
         ok &= ck["steps"] == 3 and all(torch.equal(v, rep.model.state_dict()[k]) for k, v in ck["model"].items())
+        # defaults with more than one rank: sharded; the multicast kernels only on an NCCL group (this one is gloo)
+        auto = ReedTrainer(_tiny_model(), None, precision="bf16")
+        ok &= auto.shard and auto.nvls is None and all(b.sharded == (b.name != "outer") for b in auto.state.buckets)
         out[rank] = bool(ok)
     finally:
         dist.destroy_process_group()
