@@ -24,6 +24,7 @@ def main():
     ap.add_argument("--only", default=None, help="substring filter on the case name")
     ap.add_argument("--no-flush", action="store_true", help="leave L2 warm between iterations")
     ap.add_argument("--bn", type=int, default=0, help="pin the tile width (128/192/256)")
+    ap.add_argument("--cg", type=int, default=0, help="pin the cta_group (1 / 2); 0 = planner's choice")
     ap.add_argument("--cublas", action="store_true",
                     help="also time torch.matmul (cuBLAS, no epilogue) on the same operands: a yardstick, not the product path")
     args = ap.parse_args()
@@ -31,7 +32,8 @@ def main():
     D = {"xl": 1152, "b": 768, "l": 1024, "s": 384}[args.model]
     M, T = args.tokens, 256
     dev = "cuda"
-    ops.set_backends(gemm=ops.BACKEND_TENSOR + ({0: 0, 128: 1, 192: 2, 256: 3}[args.bn] << 3))
+    ops.set_backends(gemm={0: ops.BACKEND_TENSOR, 1: ops.BACKEND_TENSOR_CG1, 2: ops.BACKEND_TENSOR_CG2}[args.cg]
+                     + ({0: 0, 128: 1, 192: 2, 256: 3}[args.bn] << 3))
     bf = torch.bfloat16
     r = lambda *s, dt=bf: (torch.randn(*s, device=dev) * 0.05).to(dt)
     flush = torch.zeros(64 << 20, dtype=torch.int32, device=dev)

@@ -43,6 +43,36 @@ class _Join:
         torch.cuda.current_stream().wait_event(self.event)
 
 
+def _enable_group(symm, group):
+    """Needed by older 2.x releases, a deprecated no-op in newer ones."""
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        try:
+            symm.enable_symm_mem_for_group(group.group_name)
+        except Exception:
+            pass
+
+
+def multicast_available(group, device) -> bool:
+    """Collective: can this process group map symmetric memory with an NVSwitch multicast address?  Every rank gets the
+    same answer (the trainer picks its exchange path from it when the caller did not choose)."""
+    import torch.distributed as dist
+    ok = 1
+    try:
+        import torch.distributed._symmetric_memory as symm
+        g = group if group is not None else dist.group.WORLD
+        _enable_group(symm, g)
+        probe = symm.empty(1024, dtype=torch.float32, device=device)
+        handle = symm.rendezvous(probe, g)
+        ok = 1 if handle.multicast_ptr else 0
+    except Exception:
+        ok = 0
+    flag = torch.tensor([ok], device=device, dtype=torch.int32)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+    return bool(int(flag))
+
+
 class NvlsExchange:
     def __init__(self, group=None, ctas: int = 16):
         import torch.distributed._symmetric_memory as symm
@@ -51,10 +81,7 @@ class NvlsExchange:
         self.ctas = ctas
         self.stream: Optional[torch.cuda.Stream] = None
         self.handles = {}
-        try:                                      # needed by older 2.x releases, a no-op / deprecated in newer ones
-            symm.enable_symm_mem_for_group(self.group.group_name)
-        except Exception:
-            pass
+        _enable_group(symm, self.group)
 
     # -- allocation hook for trainer.FlatState ---------------------------------------------------------------------
     def alloc(self, kind: str, bucket, numel: int, dtype, device):

@@ -263,6 +263,13 @@ class ReedTrainer:
             shard_optimizer = world > 1
         if nvls is None:                       # our own multicast kernels need bf16 operands and an NCCL (NVSwitch) group
             nvls = bool(shard_optimizer) and world > 1 and precision == "bf16" and dist.get_backend(group) == "nccl"
+            if nvls:                           # not chosen by the caller: fall back to NCCL collectives where the fabric has no multicast
+                from .nvls import multicast_available
+                nvls = multicast_available(group, next(model.parameters()).device)
+                if not nvls and dist.get_rank(group) == 0:
+                    import warnings
+                    warnings.warn("reed_b200: NVSwitch multicast is not available to this process group; the sharded step uses "
+                                  "NCCL reduce-scatter / all-gather instead of the multimem kernels")
         self.shard = bool(shard_optimizer) and world > 1
         self.precision = precision
         # nvls (needs shard_optimizer, bf16 operands, NCCL group on one NVSwitch domain): the reduce-scatter and the
