@@ -62,7 +62,11 @@ int reed_gemm_wgrad_bias(const void* dy, int64_t ld_dy, const void* x_ext, int64
 
 /* Multi-head attention, non-causal, scale head_dim^-0.5, over the packed qkv GEMM output.
  * Replaces timm Attention.forward's reshape/permute + F.scaled_dot_product_attention (models/sit.py:13,114-118,134).
- *   qkv [B,T,3,H,hd] (act dtype) -> o [B,T,H,hd] (act dtype), lse [B,H,T] fp32 (saved for backward). */
+ *   qkv [B,T,3,H,hd] (act dtype) -> o [B,T,H,hd] (act dtype), lse [B,H,T] fp32 (saved for backward).
+ *   backend: 0 auto - bf16 with T = 128 n and head_dim 64 / 72 runs the flash-style tcgen05 kernels (P in tensor memory;
+ *   the backward is one kernel over clusters of T/128 CTAs with a shared-memory ring for dQ), other bf16 shapes the
+ *   mma.sync or SIMT kernels, fp32 the SIMT kernels; 1 force SIMT; 2 require a tensor-core kernel; 3 require mma.sync;
+ *   4 / 5 require the tcgen05 kernels. */
 int reed_attn_fwd(int act_dtype, const void* qkv, void* o, void* lse, int B, int T, int H, int hd, int backend,
                   void* stream);
 /* dqkv [B,T,3,H,hd] from d_o [B,T,H,hd]; delta [B,H,T] fp32 is workspace (rowsum(dO*O)). */
@@ -105,7 +109,8 @@ int reed_gate_bwd(const void* dxn, const void* y, int act_dtype, const void* gat
                   void* dy, void* dgate, void* dbias, int M, int D, void* stream);
 /* out[n] += sum_m src[m,n]  (bias gradients). */
 int reed_colsum(const void* src, int act_dtype, int64_t ld, void* out, int M, int N, void* stream);
-/* op 0: dtype cast; op 1: SiLU then cast (the SiLU in front of every adaLN linear, models/sit.py:126,149). */
+/* op 0: dtype cast; op 1: SiLU then cast (the SiLU in front of every adaLN linear, models/sit.py:126,149); op 2: exact
+ * (erf) GELU then cast (nn.GELU() of the DINOv2 target encoder's MLP, utils.py:92-105). */
 int reed_unary(const void* in, int in_dtype, void* out, int out_dtype, int op, int64_t n, void* stream);
 /* dx = dy * act'(h); act 1 = GELU(tanh), 2 = SiLU. */
 int reed_act_bwd(const void* dy, int d_dtype, const void* h, int h_dtype, void* dx, int act, int64_t n, void* stream);
