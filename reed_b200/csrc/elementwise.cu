@@ -565,13 +565,12 @@ static int row_bwd_launch(RowBwdParams p, int threads, cudaStream_t st) {
   }
   // one balanced wave: as many CTAs as are resident at once (shared-memory / thread bound), equal row ranges that
   // may cross sample boundaries (the kernel flushes its column partials when the group changes)
-  static const int forced = getenv("REED_ROWS_PER_CTA") ? atoi(getenv("REED_ROWS_PER_CTA")) : 0;
   int per_sm = (220 * 1024) / (smem + 1024);
   const int by_threads = 2048 / threads;
   if (per_sm > by_threads) per_sm = by_threads;
   if (per_sm > 4) per_sm = 4;
   if (per_sm < 1) per_sm = 1;
-  int rows = forced > 0 ? forced : ceil_div(p.M, row_sm_count() * per_sm);
+  int rows = ceil_div(p.M, row_sm_count() * per_sm);
   if (rows < 1) rows = 1;
   p.rows_per_cta = rows;
   kernel<<<ceil_div(p.M, rows), threads, smem, st>>>(p);

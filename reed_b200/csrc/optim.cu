@@ -121,12 +121,7 @@ extern "C" int reed_adamw_ema(void* p, const void* g, void* m, void* v, void* em
   a.bias_c1 = (float)(1.0 - pow((double)beta1, (double)step));
   a.bias_c2_sqrt = (float)sqrt(1.0 - pow((double)beta2, (double)step));
   a.ema_decay = ema_decay; a.grad_scale = grad_scale; a.step_dev = (const int*)step_dev;
-  // profiling knobs (profiles/exp_overlap.py): CTA size / grid of the optimizer pass when it shares SMs with a GEMM
-  static const int threads = getenv("REED_ADAMW_THREADS") ? atoi(getenv("REED_ADAMW_THREADS")) : 256;
-  static const int grid_cap = getenv("REED_ADAMW_GRID") ? atoi(getenv("REED_ADAMW_GRID")) : 0;
-  int grid = opt_grid(n / 4);
-  if (grid_cap > 0 && grid > grid_cap) grid = grid_cap;
-  adamw_ema_kernel<<<grid, threads, 0, (cudaStream_t)stream>>>(a);
+  adamw_ema_kernel<<<opt_grid(n / 4), 256, 0, (cudaStream_t)stream>>>(a);
   REED_LAUNCH_CHECK();
   return 0;
 }
