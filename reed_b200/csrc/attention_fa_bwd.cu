@@ -301,12 +301,16 @@ attn_fa_bwd_kernel(const __grid_constant__ AttnMaps maps, const float* __restric
         item_bh(n, b, h);
         mbar_wait(bars + kStageFull, (uint32_t)n & 1u);
         const int row0 = b * T + (int)rank * kRows;
-        store_tile<HD>(&maps.out_main, &maps.out_tail8, sbase + CF::kOffRecv, h, row0);
+        // dK / dV first, as their own bulk group: the K/V set they are staged in is what the next-but-one item's operand
+        // prefetch waits for; the dQ store (receive buffer) follows
         store_tile<HD>(&maps.out_main, &maps.out_tail8, kv_slot(n, 1), 2 * H + h, row0);
         store_tile<HD>(&maps.out_main, &maps.out_tail8, kv_slot(n, 0), H + h, row0);
         tma_store_commit();
-        tma_store_wait_read();                        // the three stores have read their staging
+        store_tile<HD>(&maps.out_main, &maps.out_tail8, sbase + CF::kOffRecv, h, row0);
+        tma_store_commit();
+        asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");      // the dK / dV stores have read their staging
         mbar_arrive(bars + kKvEmpty + (n & 1));
+        tma_store_wait_read();                        // ... and the dQ store
         if (nst > 1) mbar_arrive_remote_release(remote_credit);       // the right neighbour may send into our buffer again
         mbar_arrive(bars + kStoreDone);
       }
