@@ -192,24 +192,26 @@ int gemm_tcgen05(const void* A, int64_t lda, int a_mn, const void* B, int64_t ld
   if (a_mn) { if (make_map(&ma, A, K, M, lda, 64)) return 1; } else { if (make_map(&ma, A, M, K, lda, 128)) return 1; }
   if (b_mn) { if (make_map(&mb, B, K, N, ldb, 64)) return 1; } else { if (make_map(&mb, B, N, K, ldb, p.bn / p.cg)) return 1; }
   // TMA epilogue (epilogue_loop_tma): bf16 D with none / activation / activation-gradient, fp32 D with gate+residual
-  static const int tma_epi_on = getenv("REED_TMA_EPI") ? atoi(getenv("REED_TMA_EPI")) : 7;
+  static const int tma_epi_on = getenv("REED_TMA_EPI") ? atoi(getenv("REED_TMA_EPI")) : 15;
   EpiMaps em;
   const EpiMaps* emp = nullptr;
   const bool act_kind = ep.kind == kEpiNone || ep.kind == kEpiGelu || ep.kind == kEpiSilu || ep.kind == kEpiDGelu || ep.kind == kEpiDSilu;
   const bool want_o2 = ep.out2 != nullptr && (ep.kind == kEpiGelu || ep.kind == kEpiSilu || ep.kind == kEpiGateRes);
   const bool has_aux = ep.kind == kEpiDGelu || ep.kind == kEpiDSilu || ep.kind == kEpiGateRes;
   // REED_TMA_EPI: bit 0 = activation-gradient kinds (fused operand), bit 1 = activation kinds, bit 2 = plain bf16 stores
-  // bit 3 = gate+residual (fp32 D, 16-column chunks; off by default: measured equal to the register path, whose
-  // exposed cost on these two-round GEMMs is the HBM traffic of the last round, not operand latency)
+  // bit 3 = gate+residual (fp32 D updated in place in a ring of residual boxes, epilogue_loop_tma_gateres) - for short
+  // reductions only (attn.proj): the ring takes shared memory from the operand pipeline, and a long main loop (mlp.fc2)
+  // loses more to a shallower pipeline than its last tile's epilogue gains (REED_GATERES_MAX_K: profiling knob)
+  static const int gateres_max_k = getenv("REED_GATERES_MAX_K") ? atoi(getenv("REED_GATERES_MAX_K")) : 2048;
   const int kind_bit = ep.kind == kEpiGateRes ? 8 : ((ep.kind == kEpiDGelu || ep.kind == kEpiDSilu) ? 1 : ((ep.kind == kEpiGelu || ep.kind == kEpiSilu) ? 2 : 4));
-  const bool gate_res = ep.kind == kEpiGateRes && d_dtype == kF32 && ep.rows_per_group % 32 == 0 && N % 16 == 0;
+  const bool gate_res = ep.kind == kEpiGateRes && d_dtype == kF32 && ep.rows_per_group % 32 == 0 && K <= gateres_max_k;
   bool tma = (tma_epi_on & kind_bit) && !p.stream_k && !ep.accumulate && ((d_dtype == kBF16 && act_kind) || gate_res) &&
              tma_ok_ptr(D, ldd, d_dtype == kF32 ? 4 : 2) && (!want_o2 || tma_ok_ptr(ep.out2, ep.ld_out2, 2)) &&
              (!has_aux || tma_ok_ptr(ep.aux, ep.ld_aux, ep.kind == kEpiGateRes ? 4 : 2)) &&
              (ep.bias == nullptr || ((uintptr_t)ep.bias & 15) == 0) &&
              (ep.kind != kEpiGateRes || (((uintptr_t)ep.gate & 15) == 0 && ep.ld_gate % 4 == 0));
   if (tma) {
-    const int bw = gate_res ? 16 : 32;     // chunk width of the epilogue variant
+    const int bw = 32;                     // chunk width of the TMA epilogues
     if (make_epi_map(&em.d, D, d_dtype, M, N, ldd, bw)) return 1;
     if (want_o2) { if (make_epi_map(&em.o2, ep.out2, kBF16, M, N, ep.ld_out2, bw)) return 1; } else em.o2 = em.d;
     if (has_aux) { if (make_epi_map(&em.aux, ep.aux, ep.kind == kEpiGateRes ? kF32 : kBF16, M, N, ep.ld_aux, bw)) return 1; } else em.aux = em.d;

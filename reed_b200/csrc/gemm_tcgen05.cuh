@@ -46,7 +46,7 @@ struct GemmCfg {
   static constexpr int kStagingBytes = kEpiWarps * 32 * kStagePitch * 4;   // epilogue region of the register/LSU epilogue
   static constexpr int kTmaEpiBytes = kEpiWarps * 8192;                    // epilogue region of the TMA epilogue ...
   static constexpr int kTmaEpiAuxBytes = kEpiWarps * 10240;                // ... with a fused global operand
-  static constexpr int kBarBytes = 512;
+  static constexpr int kBarBytes = 1024;
   // shared memory = 1024 (alignment slack) + stages * kStageBytes + epilogue region + barriers
   static constexpr int stages_for(int epi_bytes) {
     int s = (227 * 1024 - 1024 - epi_bytes - kBarBytes) / kStageBytes;
@@ -495,31 +495,26 @@ __device__ __forceinline__ void epilogue_loop_tma(const EpiParams& ep, const Epi
 }
 
 // TMA epilogue of the adaLN-Zero gate + residual GEMMs (attn.proj / mlp.fc2, sit.py:134-135): fp32 D = res + gate * bf16(y),
-// y = acc + bias -> out2 (bf16).  Chunks are 16 columns wide so that three fp32 residual boxes ([32 x 16], 2 KB,
-// SWIZZLE_64B) and two bf16 y boxes ([32 x 16], 1 KB, SWIZZLE_32B) fit the 8 KB per-warp region that keeps the
-// pipeline at full depth.  The residual box is requested two chunks ahead, updated IN PLACE (thread = row) and
-// stored back by TMA; a slot is re-requested only after the store that last used it has read it.
-// Bias and gate ride in one register per chunk: lanes 0-15 hold bias[col0 + l], lanes 16-31 gate[g, col0 + l - 16].
-__device__ __forceinline__ uint32_t sw32(uint32_t base, int r, int j) { return base + r * 32 + ((j ^ ((r >> 2) & 1)) << 4); }
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
-  uint32_t* r = reinterpret_cast<uint32_t*>(v);
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr)
-      : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
+// y = acc + bias -> out2 (bf16).  Two things bound this epilogue.  (1) The TMA unit of an SM serves about one box row
+// (<= 128 bytes) per 4 cycles, whatever the row length: 16-column boxes (64-byte rows, the first version) capped the
+// epilogue at 3 TB/s chip-wide, so chunks are 32 columns - 128-byte fp32 rows (SWIZZLE_128B), 64-byte bf16 rows.
+// (2) Residual bytes in flight: every warp owns a ring of R residual boxes ([32 x 32] fp32, 4 KB), the requests for the
+// next R - 1 chunks outstanding while one is worked on, across tile boundaries; R is a launch parameter (host: as many as leave three operand stages).  A box is
+// updated IN PLACE (thread = row) and stored back by TMA; its slot is re-requested one chunk later, once the store has
+// read it.  y leaves through one [32 x 32] bf16 box (2 KB).  Shared memory is what this epilogue competes for with the
+// operand pipeline (fc2: 6 -> 3 stages cost 72 -> 89 us of main loop), hence the lean ring: R = 2, 10 KB per warp.
+// Bias and gate ride in one register each per chunk: lane l holds bias[col0 + l] / gate[g, col0 + l].
+constexpr int kGateResSlotBytes = 4096;
+constexpr int kGateResMaxSlots = 8;
+__host__ __device__ constexpr int gateres_warp_bytes(int R) { return R * kGateResSlotBytes + 2048; }
 
 template <int CG, int BN>
 __device__ __forceinline__ void epilogue_loop_tma_gateres(const EpiParams& ep, const EpiMaps& em, int M, int N, int tiles_n,
                                                           uint32_t rank, Sched sched, uint32_t tmem_base, uint32_t wbuf,
                                                           uint64_t* auxbar, uint64_t* tfull, uint64_t* tempty, int q,
-                                                          int half, int lane) {
-  constexpr int BMT = BM * CG, W = 16, NCH = BN / W, kSlots = 3, kLook = 2, kSlotBytes = 2048;
-  constexpr int kOut2Off = kSlots * kSlotBytes;
+                                                          int half, int lane, int R) {
+  constexpr int BMT = BM * CG, W = kStageCols, NCH = BN / W;
+  const uint32_t out2_base = wbuf + R * kGateResSlotBytes;
   auto my_chunks = [&](const Seg& sgm) {
     const int width = N - (sgm.tile % tiles_n) * BN;
     const int nvalid = width >= BN ? NCH : (width + W - 1) / W;
@@ -527,77 +522,84 @@ __device__ __forceinline__ void epilogue_loop_tma_gateres(const EpiParams& ep, c
   };
   auto row0_of = [&](const Seg& sgm) { return (sgm.tile / tiles_n) * BMT + (int)rank * BM + q * 32; };
   auto col0_of = [&](const Seg& sgm, int k) { return (sgm.tile % tiles_n) * BN + (half + 2 * k) * W; };
-  auto load_bg = [&](const Seg& ts, int k) {
-    const int c = col0_of(ts, k) + (lane & 15);
+  auto load_bias = [&](const Seg& ts, int k) {
+    const int c = col0_of(ts, k) + lane;
+    return (ep.bias != nullptr && c < N) ? __ldg(ep.bias + c) : 0.f;
+  };
+  auto load_gate = [&](const Seg& ts, int k) {
+    const int c = col0_of(ts, k) + lane;
     if (c >= N) return 0.f;
-    if (lane < 16) return ep.bias != nullptr ? __ldg(ep.bias + c) : 0.f;
     const int r0 = row0_of(ts);
     return __ldg(ep.gate + (int64_t)((r0 < M ? r0 : M - 1) / ep.rows_per_group) * ep.ld_gate + c);
   };
   int acc = 0;
   uint32_t acc_phase = 0;
-  float bg_next = 0.f;
-  int gbase = 0, issued = 0;
+  float b_next = 0.f, g_next = 0.f;
+  int issued = 0;                      // residual requests made, counted from the current tile's first chunk
+  int ld_slot = 0;                     // ring slot of the next request
+  int use_slot = 0;                    // ring slot of the chunk in work ...
+  uint32_t use_phase = 0;              // ... its mbarrier parity
   Seg sg, nx;
   bool have = sched.next(sg);
   bool bg_ready = false;
   while (have) {
     const bool have_next = sched.next(nx);
     const int cnt = my_chunks(sg), cntn = have_next ? my_chunks(nx) : 0;
-    if (cnt > 0 && !bg_ready) bg_next = load_bg(sg, 0);
+    if (cnt > 0 && !bg_ready) { b_next = load_bias(sg, 0); g_next = load_gate(sg, 0); }
     bg_ready = false;
     const int row0 = row0_of(sg);
-    if (have_next)
-      epilogue_l2_prefetch<BN>((const char*)ep.aux, ep.ld_aux * 4, 4, M, N, (nx.tile / tiles_n) * BMT + (int)rank * BM,
-                               (nx.tile % tiles_n) * BN, q, half, lane);
     const uint32_t taddr = tmem_base + acc * BN + ((uint32_t)(q * 32) << 16);
+    // keep requests for the chunks p .. p + R - 1 outstanding (running into the next tile at the end of this one).  The
+    // caller has made sure the store of chunk p - 1 has read its slot and the y box (wait_group.read 0).
     auto top_up = [&](int p) {
-      while (issued < p + kLook + 1 && issued < cnt + cntn) {
+      while (issued < p + R && issued < cnt + cntn) {
         const bool in_next = issued >= cnt;
         const Seg& ts = in_next ? nx : sg;
         const int k = in_next ? issued - cnt : issued;
-        const int slot = (gbase + issued) % kSlots;
         if (lane == 0) {
-          bulk_wait_read<0>();      // in place: the slot fed the store of the chunk that used it last
-          const uint32_t bar = smem_u32(&auxbar[slot]);
+          const uint32_t bar = smem_u32(&auxbar[ld_slot]);
           mbar_expect_tx_u32(bar, 32 * W * 4);
-          tma_load_2d_u32(&em.aux, bar, wbuf + slot * kSlotBytes, col0_of(ts, k), row0_of(ts));
+          tma_load_2d_u32(&em.aux, bar, wbuf + ld_slot * kGateResSlotBytes, col0_of(ts, k), row0_of(ts));
         }
         ++issued;
+        if (++ld_slot == R) ld_slot = 0;
       }
     };
+    if (lane == 0) bulk_wait_read<0>();
     top_up(0);
     mbar_wait(&tfull[acc], acc_phase);
     tc_fence_after();
 #pragma unroll 1
     for (int p = 0; p < cnt; ++p) {
-      const int G = gbase + p;
       const int col0 = col0_of(sg, p);
-      const float bg = bg_next;
-      if (p + 1 < cnt) bg_next = load_bg(sg, p + 1);
-      else if (cntn > 0) { bg_next = load_bg(nx, 0); bg_ready = true; }
-      float v[16];
-      tmem_ld16(taddr + (half + 2 * p) * W, v);
-      top_up(p);
-      const int slot = G % kSlots;
-      const uint32_t ab = wbuf + slot * kSlotBytes, out2b = wbuf + kOut2Off + (G & 1) * 1024;
-      uint32_t y[8];
+      const float b_cur = b_next, g_cur = g_next;
+      if (p + 1 < cnt) { b_next = load_bias(sg, p + 1); g_next = load_gate(sg, p + 1); }
+      else if (cntn > 0) { b_next = load_bias(nx, 0); g_next = load_gate(nx, 0); bg_ready = true; }
+      const uint32_t ab = wbuf + use_slot * kGateResSlotBytes, out2b = out2_base;
+      uint32_t y[16];
+      {
+        float v[32];
+        tmem_ld32(taddr + (half + 2 * p) * W, v);
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
-        y[i] = pack_bf16x2(v[2 * i] + __shfl_sync(0xffffffffu, bg, 2 * i), v[2 * i + 1] + __shfl_sync(0xffffffffu, bg, 2 * i + 1));
-      if (lane == 0) bulk_wait_read<1>();     // the y box of this parity went out two chunks ago
+        for (int i = 0; i < 16; ++i)
+          y[i] = pack_bf16x2(v[2 * i] + __shfl_sync(0xffffffffu, b_cur, 2 * i), v[2 * i + 1] + __shfl_sync(0xffffffffu, b_cur, 2 * i + 1));
+      }
+      // the stores of the previous chunk have read the y box and their residual slot: the slot takes the request for
+      // chunk p + R - 1 now, while this chunk is still being worked on
+      if (lane == 0) bulk_wait_read<0>();
+      top_up(p);
       __syncwarp();
       if (ep.out2) {
-        sts_u4(sw32(out2b, lane, 0), y[0], y[1], y[2], y[3]);
-        sts_u4(sw32(out2b, lane, 1), y[4], y[5], y[6], y[7]);
-      }
-      mbar_wait(&auxbar[slot], (uint32_t)(G / kSlots) & 1u);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const uint32_t ra = sw64(ab, lane, j);
+        for (int j = 0; j < 4; ++j) sts_u4(sw64(out2b, lane, j), y[4 * j], y[4 * j + 1], y[4 * j + 2], y[4 * j + 3]);
+      }
+      mbar_wait(&auxbar[use_slot], use_phase);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const uint32_t ra = sw128(ab, lane, j);
         const uint4 rv = lds_u4(ra);
-        const float g0 = __shfl_sync(0xffffffffu, bg, 16 + 4 * j), g1 = __shfl_sync(0xffffffffu, bg, 17 + 4 * j);
-        const float g2 = __shfl_sync(0xffffffffu, bg, 18 + 4 * j), g3 = __shfl_sync(0xffffffffu, bg, 19 + 4 * j);
+        const float g0 = __shfl_sync(0xffffffffu, g_cur, 4 * j), g1 = __shfl_sync(0xffffffffu, g_cur, 4 * j + 1);
+        const float g2 = __shfl_sync(0xffffffffu, g_cur, 4 * j + 2), g3 = __shfl_sync(0xffffffffu, g_cur, 4 * j + 3);
         const float o0 = __uint_as_float(rv.x) + g0 * bf16_lo(y[2 * j]);
         const float o1 = __uint_as_float(rv.y) + g1 * bf16_hi(y[2 * j]);
         const float o2 = __uint_as_float(rv.z) + g2 * bf16_lo(y[2 * j + 1]);
@@ -611,6 +613,7 @@ __device__ __forceinline__ void epilogue_loop_tma_gateres(const EpiParams& ep, c
         if (ep.out2) tma_store_2d(&em.o2, out2b, col0, row0);
         bulk_commit();
       }
+      if (++use_slot == R) { use_slot = 0; use_phase ^= 1u; }
     }
     tc_fence_before();
     __syncwarp();
@@ -619,7 +622,6 @@ __device__ __forceinline__ void epilogue_loop_tma_gateres(const EpiParams& ep, c
       else mbar_arrive_cluster(mapa_u32(smem_u32(&tempty[acc]), 0));
     }
     if (++acc == 2) { acc = 0; acc_phase ^= 1; }
-    gbase += cnt;
     issued -= cnt;
     sg = nx;
     have = have_next;
@@ -634,7 +636,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                     const __grid_constant__ EpiMaps emaps, TD* __restrict__ D, int64_t ldd, int M, int N, int K,
                     EpiParams ep, int stream_k, int dbg, int stages, int epi_bytes, int tma_epi) {
   // stages / epi_bytes: pipeline depth and size of the epilogue's shared-memory region (host: GemmCfg::stages_for);
-  // tma_epi: 1 = TMA epilogue (epilogue_loop_tma; emaps valid), 0 = register / LSU epilogue
+  // tma_epi: 0 = register / LSU epilogue; 1 = TMA epilogue (epilogue_loop_tma; emaps valid); fp32 D (gate+residual):
+  // the number of residual ring slots per warp (epilogue_loop_tma_gateres)
   // stream_k: 0 = data-parallel; n >= 1 = split mode with n k-slices for the tiles of the last partial round
   // dbg (profiling only, results are garbage): 1 = no TMA (MMA does not wait for operands), 2 = no MMA issue,
   // 4 = no epilogue work (accumulators released immediately); 8 = column-major tile order (results stay correct)
@@ -655,7 +658,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   uint64_t* tfull = bars + 16;        // [2]   accumulator complete (arrives in every CTA of the pair)
   uint64_t* tempty = bars + 18;       // [2]   accumulator drained by all epilogue warps (of both CTAs; leader's copy)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
-  uint64_t* auxbars = bars + 24;      // [8 warps][4] operand boxes of the TMA epilogue landed
+  uint64_t* auxbars = bars + 24;      // [8 warps][8] operand boxes of the TMA epilogue landed
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = CG == 1 ? 0u : cluster_ctarank();
@@ -684,7 +687,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       mbar_init(&tfull[s], 1);
       mbar_init(&tempty[s], kEpiWarps * CG);
     }
-    for (int s = 0; s < kEpiWarps * 4; ++s) mbar_init(&auxbars[s], 1);
+    for (int s = 0; s < kEpiWarps * 8; ++s) mbar_init(&auxbars[s], 1);
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc<CG>(tmem_slot, Cfg::kTmemCols);
@@ -812,10 +815,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     Sched sched(stream_k, tiles_m, tiles_n, ragged, num_kb, worker, workers, (dbg >> 3) & 1);
     if (tma_epi && !(dbg & 4)) {
       const uint32_t wbuf = smem_u32(epi_region) + (warp - kFirstEpiWarp) * (epi_bytes / kEpiWarps);
-      uint64_t* ab = auxbars + (warp - kFirstEpiWarp) * 4;
+      uint64_t* ab = auxbars + (warp - kFirstEpiWarp) * 8;
 #define REED_TMA_EPI(KIND) epilogue_loop_tma<KIND, CG, BN, TD>(ep, emaps, M, N, tiles_n, rank, sched, tmem_base, wbuf, ab, tfull, tempty, q, half, lane)
       if constexpr (sizeof(TD) == 4) {
-        epilogue_loop_tma_gateres<CG, BN>(ep, emaps, M, N, tiles_n, rank, sched, tmem_base, wbuf, ab, tfull, tempty, q, half, lane);
+        epilogue_loop_tma_gateres<CG, BN>(ep, emaps, M, N, tiles_n, rank, sched, tmem_base, wbuf, ab, tfull, tempty, q, half, lane, tma_epi);
       } else {
         if (ep.kind == kEpiNone) REED_TMA_EPI(kEpiNone);
         else if (ep.kind == kEpiGelu) REED_TMA_EPI(kEpiGelu);
@@ -893,19 +896,30 @@ static int launch(const CUtensorMap& ma, const CUtensorMap& mb, void* D, int64_t
   static_assert(Cfg::stages_for(Cfg::kStagingBytes) >= 3, "pipeline too shallow");
   static_assert(!B_MN || Cfg::kBNL % 64 == 0, "MN-major B is staged in 64-column TMA boxes");
   constexpr bool kTmaFits = Cfg::stages_for(Cfg::kTmaEpiAuxBytes) >= 3;
-  const int tma_epi = (em != nullptr && kTmaFits) ? 1 : 0;
+  int tma_epi = (em != nullptr && kTmaFits) ? 1 : 0;
   const bool fused_operand = ep.kind == kEpiDGelu || ep.kind == kEpiDSilu;
-  const int epi_bytes = tma_epi ? (fused_operand ? Cfg::kTmaEpiAuxBytes : Cfg::kTmaEpiBytes) : Cfg::kStagingBytes;
+  int epi_bytes = tma_epi ? (fused_operand ? Cfg::kTmaEpiAuxBytes : Cfg::kTmaEpiBytes) : Cfg::kStagingBytes;
+  if (tma_epi && sizeof(TD) == 4) {
+    // gate+residual: residual ring slots per epilogue warp (two by default: the ring competes with the operand stages for
+    // shared memory); tile configurations whose stages are too large for that keep the register epilogue
+    // (REED_GATERES_SLOTS: profiling knob)
+    static const int want = getenv("REED_GATERES_SLOTS") ? atoi(getenv("REED_GATERES_SLOTS")) : 2;
+    int R = want < 2 ? 2 : (want > kGateResMaxSlots ? kGateResMaxSlots : want);
+    while (R > 2 && Cfg::stages_for(kEpiWarps * gateres_warp_bytes(R)) < 3) --R;
+    if (Cfg::stages_for(kEpiWarps * gateres_warp_bytes(R)) >= 3) {
+      tma_epi = R;
+      epi_bytes = kEpiWarps * gateres_warp_bytes(R);
+    } else {
+      tma_epi = 0;
+      epi_bytes = Cfg::kStagingBytes;
+    }
+  }
   const int stages = Cfg::stages_for(epi_bytes);
   const int smem = Cfg::smem_bytes(stages, epi_bytes);
   auto kernel = gemm_tcgen05_kernel<CG, BN, A_MN, B_MN, TD>;
   static bool configured = false;   // per template instance
   if (!configured) {
-    const int a = Cfg::smem_bytes(Cfg::stages_for(Cfg::kStagingBytes), Cfg::kStagingBytes);
-    const int b0 = kTmaFits ? Cfg::smem_bytes(Cfg::stages_for(Cfg::kTmaEpiBytes), Cfg::kTmaEpiBytes) : 0;
-    const int b1 = kTmaFits ? Cfg::smem_bytes(Cfg::stages_for(Cfg::kTmaEpiAuxBytes), Cfg::kTmaEpiAuxBytes) : 0;
-    const int b = b0 > b1 ? b0 : b1;
-    REED_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, a > b ? a : b));
+    REED_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     configured = true;
   }
   cudaLaunchConfig_t cfg{};

@@ -154,6 +154,30 @@ def test_gemm_tma_epilogue_many_tiles(ops, bn):
     assert _rel(got.float(), want) < 1.5e-2
 
 
+@pytest.mark.parametrize("bn", [0, 1, 2, 3])                   # planner's choice / tile width 128 / 192 / 256
+@pytest.mark.parametrize("cg", [1, 2])
+def test_gemm_gate_residual_many_tiles(ops, bn, cg):
+    """x + gate * (a W^T + b) over several tiles per persistent CTA (sit.py:134-135): the residual ring of the TMA
+    epilogue, the bias / gate look-ahead and the in-place boxes carry over tile boundaries; ragged M and N."""
+    ops.set_backends(gemm=(ops.BACKEND_TENSOR_CG1 if cg == 1 else ops.BACKEND_TENSOR_CG2) + 8 * bn)
+    for B, T, N, K in ((157, 96, 1104, 128), (40, 256, 1152, 320), (3, 32, 48, 64)):
+        M = B * T
+        a, w, _, _ = _operands(M, N, K, 0, 0, torch.bfloat16)
+        bias = _rand(N, seed=3)
+        res = _rand(M, N, seed=4)
+        gate = _rand(B, 3 * N, seed=5)[:, N:2 * N]
+        y = torch.empty(M, N, device=DEV, dtype=torch.bfloat16)
+        out = ops.gemm(a, w, out_dtype=torch.float32, bias=bias, epilogue=ops.EPI_GATE_RES, aux=res, gate=gate,
+                       rows_per_group=T, out2=y)
+        acc = a.float() @ w.float().t() + bias
+        assert _rel(y.float(), acc) < 1e-2
+        want = res + gate.repeat_interleave(T, dim=0) * y.float()
+        assert _rel(out, want) < 1e-5
+        out_b = ops.gemm(a, w, out_dtype=torch.float32, bias=bias, epilogue=ops.EPI_GATE_RES, aux=res, gate=gate,
+                         rows_per_group=T)                      # without the saved y
+        assert torch.equal(out_b, out)
+
+
 @pytest.mark.parametrize("cg", [1, 2])
 @pytest.mark.parametrize("bn", [1, 2, 3])                      # tile width 128 / 192 / 256
 @pytest.mark.parametrize("layout", [(0, 0), (0, 1), (1, 1)])
