@@ -32,7 +32,8 @@ constexpr int kGemmThreads = 352;   // warps 0-2: TMA / MMA / TMEM alloc; warps 
 constexpr int kFirstEpiWarp = 3;
 constexpr int kEpiWarps = 8;
 constexpr int kStageCols = 32;  // accumulator columns moved per tcgen05.ld
-constexpr int kStagePitch = 36; // floats; 144 B row pitch keeps float4 smem accesses conflict-free
+constexpr int kStagePitch = 32; // floats; 16-byte chunk j of row r sits at chunk j ^ (r & 7): float4 accesses stay conflict-free
+                                // without padding (4 KB per warp - the 32 KB region leaves the 256-wide tiles a sixth stage)
 
 constexpr int kEpiAccum = 6;    // internal: kEpiNone with ep.accumulate (D += acc), fp32 D
 constexpr int kEpiAtomic = 7;   // internal: stream-K partial tile, red.add into fp32 D
@@ -44,15 +45,12 @@ struct GemmCfg {
   static constexpr int kBBytes = kBNL * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kStagingBytes = kEpiWarps * 32 * kStagePitch * 4;   // epilogue region of the register/LSU epilogue
-  static constexpr int kTmaEpiBytes = kEpiWarps * 8192;                    // epilogue region of the TMA epilogue ...
-  static constexpr int kTmaEpiAuxBytes = kEpiWarps * 10240;                // ... with a fused global operand
+  static constexpr int kTmaEpiBytes = kEpiWarps * 4096;                    // epilogue region of the TMA epilogue ...
+  static constexpr int kTmaEpiAuxBytes = kEpiWarps * 8192;                 // ... with a fused global operand
   static constexpr int kBarBytes = 1024;
   // shared memory = 1024 (alignment slack) + stages * kStageBytes + epilogue region + barriers
   static constexpr int stages_for(int epi_bytes) {
     int s = (227 * 1024 - 1024 - epi_bytes - kBarBytes) / kStageBytes;
-#ifdef REED_GEMM_MAX_STAGES
-    if (s > REED_GEMM_MAX_STAGES) s = REED_GEMM_MAX_STAGES;
-#endif
     return s > 8 ? 8 : s;
   }
   static constexpr int smem_bytes(int stages, int epi_bytes) { return 1024 + stages * kStageBytes + epi_bytes + kBarBytes; }
@@ -199,7 +197,7 @@ __device__ __forceinline__ void epilogue_tile(const EpiParams& ep, TD* __restric
       // thread = accumulator row: park the 32 columns in smem ...
 #pragma unroll
       for (int j = 0; j < 8; ++j)
-        *reinterpret_cast<float4*>(st + lane * kStagePitch + j * 4) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        *reinterpret_cast<float4*>(st + lane * kStagePitch + ((j ^ (lane & 7)) << 2)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
     }
     __syncwarp();
     // ... and pick them up row-coalesced: 8 lanes cover one 32-column row segment, 4 rows per instruction.
@@ -209,7 +207,8 @@ __device__ __forceinline__ void epilogue_tile(const EpiParams& ep, TD* __restric
     const int col = n0 + c0 + cc;
     float4 fr[8];
 #pragma unroll
-    for (int it = 0; it < 8; ++it) fr[it] = *reinterpret_cast<const float4*>(st + (it * 4 + rsub) * kStagePitch + cc);
+    for (int it = 0; it < 8; ++it)
+      fr[it] = *reinterpret_cast<const float4*>(st + (it * 4 + rsub) * kStagePitch + (((lane & 7) ^ ((it * 4 + rsub) & 7)) << 2));
     const bool full = row_base + 32 <= M && n0 + c0 + kStageCols <= N;
     auto row_op = [&](int it) {
       const int row = row_base + it * 4 + rsub;
@@ -296,9 +295,10 @@ __device__ __forceinline__ void epilogue_l2_prefetch(const char* aux, int64_t pi
 //   * tcgen05.ld leaves thread = accumulator row; the math runs in that layout and reads the operand row from the
 //     swizzled box (conflict-free 16-byte accesses);
 //   * results are packed into a swizzled [32 x 32] box per output and written back by TMA stores (bulk groups; a box
-//     is reused once the store issued two chunks earlier has read it).  The residual box is updated in place.
-// bf16 outputs only (none / activation / activation-gradient).  Per-warp region: [operand slots x3][D boxes x2]
-// [out2 boxes x2] - 10 KB with a fused operand, 8 KB without.
+//     is reused once the store of the previous chunk has read it - a second set of boxes would hide that wait, but
+//     shared memory buys more as operand stages: these GEMMs lose 5-20 % going from 6 to 4 stages).
+// bf16 outputs only (none / activation / activation-gradient).  Per-warp region: [operand slots x3][D box][out2 box]
+// - 8 KB with a fused operand, 4 KB without.
 // ------------------------------------------------------------------------------------------------
 template <int KIND> struct TmaEpi {
   static constexpr bool kAuxBf16 = KIND == kEpiDGelu || KIND == kEpiDSilu;
@@ -308,8 +308,8 @@ template <int KIND> struct TmaEpi {
   static constexpr int kLook = 2;                           // operand requests in flight ahead of the chunk in work
   static_assert(kSlots == 0 || kSlots == kLook + 1, "a ring slot is reused by the request kLook + 1 chunks later");
   static constexpr int kSlotBytes = kAuxBf16 ? 2048 : 4096;
-  static constexpr int kOutOff = kSlots * kSlotBytes;       // bf16 D boxes, 2 x 2 KB (unused for in-place fp32)
-  static constexpr int kOut2Off = kOutOff + (kAuxF32 ? 0 : 4096);
+  static constexpr int kOutOff = kSlots * kSlotBytes;       // bf16 D box, 2 KB
+  static constexpr int kOut2Off = kOutOff + 2048;
 };
 
 // 16-byte chunk j of row r inside a [32 x 64 B] SWIZZLE_64B box / a [32 x 128 B] SWIZZLE_128B box
@@ -425,11 +425,10 @@ __device__ __forceinline__ void epilogue_loop_tma(const EpiParams& ep, const Epi
         for (int i = 0; i < 32; ++i) v[i] += __shfl_sync(0xffffffffu, b_cur, i);
       }
       top_up(p);                    // keeps kLook operand boxes in flight (into the next tile at the end of this one)
-      const int ob = G & 1;
-      // the D / out2 boxes of this parity were handed to the store issued two chunks ago
-      if (lane == 0) bulk_wait_read<1>();
+      // the D / out2 boxes were handed to the store of the previous chunk
+      if (lane == 0) bulk_wait_read<0>();
       __syncwarp();
-      const uint32_t outb = wbuf + E::kOutOff + ob * 2048, out2b = wbuf + E::kOut2Off + ob * 2048;
+      const uint32_t outb = wbuf + E::kOutOff, out2b = wbuf + E::kOut2Off;
       if constexpr (KIND == kEpiNone) {
 #pragma unroll
         for (int j = 0; j < 4; ++j)
@@ -914,7 +913,8 @@ static int launch(const CUtensorMap& ma, const CUtensorMap& mb, void* D, int64_t
       epi_bytes = Cfg::kStagingBytes;
     }
   }
-  const int stages = Cfg::stages_for(epi_bytes);
+  static const int max_stages = getenv("REED_GEMM_MAX_STAGES") ? atoi(getenv("REED_GEMM_MAX_STAGES")) : 8;   // profiling knob
+  const int stages = Cfg::stages_for(epi_bytes) < max_stages ? Cfg::stages_for(epi_bytes) : (max_stages < 2 ? 2 : max_stages);
   const int smem = Cfg::smem_bytes(stages, epi_bytes);
   auto kernel = gemm_tcgen05_kernel<CG, BN, A_MN, B_MN, TD>;
   static bool configured = false;   // per template instance
