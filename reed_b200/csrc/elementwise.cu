@@ -75,6 +75,9 @@ __global__ void __launch_bounds__(kLnWarps * 32) ln_modulate_fwd_kernel(
 #pragma unroll
     for (int s = 0; s < kLnStages; ++s) row_bar_init(&bars[warp][s]);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  pdl_wait();     // launched programmatically: everything above ran under the tail of the previous kernel
+  if (lane == 0) {
 #pragma unroll
     for (int s = 0; s < kLnStages; ++s) {
       const int row = first + s * kLnWarps;
@@ -198,6 +201,9 @@ __device__ __forceinline__ void red_add_v4(float* p, const F4& f) {
 }
 
 constexpr int kRowMaxThreads = 384;
+constexpr int kRowV = 3;            // float4 column groups per thread
+constexpr int kRowMaxTeams = 12;
+constexpr int kRowMaxStages = 4;
 
 // bytes of one row's operands in the shared-memory ring of row_bwd_kernel
 template <typename TA, bool LN, bool GATE>
@@ -205,13 +211,22 @@ __host__ __device__ inline int row_slot_bytes(int D, bool has_res) {
   return (LN ? D * (int)sizeof(TA) + D * 4 : 0) + (has_res ? D * 4 : 0) + (GATE ? D * (int)sizeof(TA) : 0);
 }
 
+// Work split (round 2): a row is owned by a TEAM of `team_threads` threads (D / 12 rounded up to whole warps: 3 warps at
+// D = 1152), every thread holding kRowV float4 column groups of it; a CTA runs 384 / team_threads teams side by side on
+// interleaved rows (r0 + team, r0 + team + teams, ...), each with its own ring of `stages` row slots filled by bulk copies
+// and its own named barrier.  With one float4 per thread and the whole CTA on one row (round 1) the per-row overhead
+// - two shuffle reductions, a CTA barrier, the cross-warp sum, address arithmetic - was 4/5 of the 256 instructions a
+// warp issued per row and the kernels ran at 0.56-0.67 issue utilisation, 0.65-0.73 of the HBM rate (ncu,
+// profiles/r02_ncu_row_bwd.txt); twelve elements per thread amortise it.
 template <typename TA, int V, bool LN, bool GATE>
-__global__ void __launch_bounds__(kRowMaxThreads) row_bwd_kernel(const RowBwdParams p) {
+__global__ void __launch_bounds__(kRowMaxThreads, 1) row_bwd_kernel(const RowBwdParams p, int team_threads, int stages) {
   pdl_launch();   // dependents (the next GEMM of the stream) may start their prologue
   extern __shared__ __align__(128) uint8_t row_smem[];
-  __shared__ uint64_t full[kRowStages];
+  __shared__ uint64_t full[kRowMaxTeams * kRowMaxStages];
   __shared__ float2 red[2][kRowMaxThreads / 32];
-  const int NT = blockDim.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = NT >> 5;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int teams = blockDim.x / team_threads, team = tid / team_threads, t = tid - team * team_threads;
+  const int wpt = team_threads >> 5, warp0 = team * wpt;
   const int D = p.D;
   const int r0 = blockIdx.x * p.rows_per_cta;
   const int r1 = min(r0 + p.rows_per_cta, p.M);
@@ -223,25 +238,30 @@ __global__ void __launch_bounds__(kRowMaxThreads) row_bwd_kernel(const RowBwdPar
   const int o_r = o_x + (LN ? D * 4 : 0);
   const int o_y = o_r + (has_res ? D * 4 : 0);
   const int slot_bytes = o_y + (GATE ? D * (int)sizeof(TA) : 0);
+  uint8_t* ring = row_smem + (size_t)team * stages * slot_bytes;
+  uint64_t* bars = full + team * kRowMaxStages;
 
-  auto issue = [&](int row, int slot) {       // thread 0: all operands of one row -> ring slot
-    uint8_t* dst = row_smem + (size_t)slot * slot_bytes;
+  auto issue = [&](int row, int slot) {       // team thread 0: all operands of one row -> ring slot
+    uint8_t* dst = ring + (size_t)slot * slot_bytes;
     const int64_t base = (int64_t)row * D;
-    row_bar_expect(&full[slot], (uint32_t)slot_bytes);
+    row_bar_expect(&bars[slot], (uint32_t)slot_bytes);
     if constexpr (LN) {
-      row_bulk_load(dst, reinterpret_cast<const TA*>(p.dout) + base, (uint32_t)(D * sizeof(TA)), &full[slot]);
-      row_bulk_load(dst + o_x, p.x + base, (uint32_t)D * 4u, &full[slot]);
+      row_bulk_load(dst, reinterpret_cast<const TA*>(p.dout) + base, (uint32_t)(D * sizeof(TA)), &bars[slot]);
+      row_bulk_load(dst + o_x, p.x + base, (uint32_t)D * 4u, &bars[slot]);
     }
-    if (has_res) row_bulk_load(dst + o_r, p.dres + base, (uint32_t)D * 4u, &full[slot]);
-    if constexpr (GATE) row_bulk_load(dst + o_y, reinterpret_cast<const TA*>(p.y) + base, (uint32_t)(D * sizeof(TA)), &full[slot]);
+    if (has_res) row_bulk_load(dst + o_r, p.dres + base, (uint32_t)D * 4u, &bars[slot]);
+    if constexpr (GATE) row_bulk_load(dst + o_y, reinterpret_cast<const TA*>(p.y) + base, (uint32_t)(D * sizeof(TA)), &bars[slot]);
   };
-  if (tid == 0) {
-#pragma unroll
-    for (int s = 0; s < kRowStages; ++s) row_bar_init(&full[s]);
+  auto team_sync = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(1 + team), "r"(team_threads) : "memory"); };
+  const int first = r0 + team;
+  if (t == 0) {
+    for (int s = 0; s < stages; ++s) row_bar_init(&bars[s]);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-#pragma unroll
-    for (int s = 0; s < kRowStages; ++s)
-      if (r0 + s < r1) issue(r0 + s, s);
+  }
+  pdl_wait();     // launched programmatically: everything above ran under the tail of the previous kernel
+  if (t == 0) {
+    for (int s = 0; s < stages; ++s)
+      if (first + s * teams < r1) issue(first + s * teams, s);
   }
   __syncthreads();
 
@@ -251,7 +271,7 @@ __global__ void __launch_bounds__(kRowMaxThreads) row_bwd_kernel(const RowBwdPar
   F4 a_sh[LN ? V : 1], a_sc[LN ? V : 1], a_g[GATE ? V : 1], a_b[GATE ? V : 1];
 #pragma unroll
   for (int i = 0; i < V; ++i) {
-    col[i] = (tid + i * NT) * 4;
+    col[i] = (t + i * team_threads) * 4;
     ok[i] = col[i] < D;
   }
   auto load_group = [&](int g) {              // per-group modulation vectors; column partial sums restart
@@ -292,27 +312,27 @@ __global__ void __launch_bounds__(kRowMaxThreads) row_bwd_kernel(const RowBwdPar
     }
   };
 
-  int g = r0 / p.rows_per_group;
+  if (first >= r1) return;                    // (after the CTA barrier; a team without rows owns no named barrier traffic)
+  int g = first / p.rows_per_group;
+  int g_end = (g + 1) * p.rows_per_group;     // first row of the next group
   load_group(g);
   float mean_n = 0.f, rstd_n = 0.f;
-  if constexpr (LN) {
-    if (r0 < r1) { mean_n = p.mean[r0]; rstd_n = p.rstd[r0]; }
-  }
-  int buf = 0, it = 0;
-  for (int row = r0; row < r1; ++row, ++it) {
-    const int gr = row / p.rows_per_group;
-    if (gr != g) {                            // the CTA's row range crosses into the next sample
+  if constexpr (LN) { mean_n = p.mean[first]; rstd_n = p.rstd[first]; }
+  int buf = 0, slot = 0;
+  uint32_t parity = 0;
+  for (int row = first; row < r1; row += teams) {
+    if (row >= g_end) {                       // the team's rows cross into the next sample (rows_per_group >= teams or not)
       flush_group(g);
-      g = gr;
+      g = row / p.rows_per_group;
+      g_end = (g + 1) * p.rows_per_group;
       load_group(g);
     }
     const float mean = mean_n, rstd = rstd_n;
     if constexpr (LN) {
-      if (row + 1 < r1) { mean_n = p.mean[row + 1]; rstd_n = p.rstd[row + 1]; }
+      if (row + teams < r1) { mean_n = p.mean[row + teams]; rstd_n = p.rstd[row + teams]; }
     }
-    const int slot = it % kRowStages;
-    row_bar_wait(&full[slot], (uint32_t)(it / kRowStages) & 1u);
-    const uint8_t* src = row_smem + (size_t)slot * slot_bytes;
+    row_bar_wait(&bars[slot], parity);
+    const uint8_t* src = ring + (size_t)slot * slot_bytes;
     F4 d[LN ? V : 1], xv[LN ? V : 1], gin[V], yv[GATE ? V : 1];
 #pragma unroll
     for (int i = 0; i < V; ++i) {
@@ -347,22 +367,25 @@ __global__ void __launch_bounds__(kRowMaxThreads) row_bwd_kernel(const RowBwdPar
       }
       s1 = warp_sum(s1);
       s2 = warp_sum(s2);
-      if (lane == 0) red[buf][warp] = make_float2(s1, s2);
+      if (wpt > 1 && lane == 0) red[buf][warp] = make_float2(s1, s2);
     }
-    // one barrier per row: every thread has copied its operands out of the slot (it can be refilled) and, for LN,
-    // the per-warp partial sums are visible
-    __syncthreads();
-    if (tid == 0 && row + kRowStages < r1) issue(row + kRowStages, slot);
+    // one team barrier per row: every thread of the team has copied its operands out of the slot (it can be refilled)
+    // and, for LN, the per-warp partial sums are visible
+    team_sync();
+    if (t == 0 && row + stages * teams < r1) issue(row + stages * teams, slot);
+    if (++slot == stages) { slot = 0; parity ^= 1u; }
     const int64_t base = (int64_t)row * D;
     if constexpr (LN) {
-      s1 = 0.f;
-      s2 = 0.f;
-      for (int w = 0; w < nwarps; ++w) {
-        const float2 t = red[buf][w];
-        s1 += t.x;
-        s2 += t.y;
+      if (wpt > 1) {
+        s1 = 0.f;
+        s2 = 0.f;
+        for (int w = 0; w < wpt; ++w) {
+          const float2 tt = red[buf][warp0 + w];
+          s1 += tt.x;
+          s2 += tt.y;
+        }
+        buf ^= 1;    // the next row uses the other slot of `red`
       }
-      buf ^= 1;    // the next row uses the other slot of `red`
       const float c1 = s1 * inv_d, c2 = s2 * inv_d;
 #pragma unroll
       for (int i = 0; i < V; ++i) {
@@ -389,7 +412,7 @@ __global__ void __launch_bounds__(kRowMaxThreads) row_bwd_kernel(const RowBwdPar
       }
     }
   }
-  if (r0 < r1) flush_group(g);
+  flush_group(g);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -525,6 +548,25 @@ static int row_sm_count() {
   return n;
 }
 
+// Launch with the programmatic-serialization attribute: the grid may become resident while the previous kernel of the
+// stream drains (its prologue - barrier init, index arithmetic - runs there); the kernel calls pdl_wait() before its
+// first global access.  REED_ROW_PDL=0: plain launches (profiling knob).
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_row_kernel(void (*kernel)(KArgs...), int grid, int block, int smem, cudaStream_t st, Args... args) {
+  static const int pdl = getenv("REED_ROW_PDL") ? atoi(getenv("REED_ROW_PDL")) : 1;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(block);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 template <typename TA, int V>
 static int ln_fwd_launch(const float* x, const float* shift, const float* scale, int64_t ld_mod, int rpg, void* out,
                          int64_t ld_out, float* mean, float* rstd, int M, int D, float eps, cudaStream_t st) {
@@ -540,8 +582,8 @@ static int ln_fwd_launch(const float* x, const float* shift, const float* scale,
   // CTAs in 1.7 waves 18.4 us, 64 rows 18.5 us)
   int rows = 32;
   while (rows > 1 && (rpg % rows != 0 || ceil_div(M, rows) < row_sm_count())) rows >>= 1;
-  kernel<<<ceil_div(M, rows), kLnWarps * 32, smem, st>>>(x, shift, scale, ld_mod, rpg, rows, (TA*)out, ld_out, mean, rstd, M, D, eps);
-  REED_LAUNCH_CHECK();
+  REED_CHECK_CUDA(launch_row_kernel(kernel, ceil_div(M, rows), kLnWarps * 32, smem, st, x, shift, scale, ld_mod, rpg, rows, (TA*)out, ld_out,
+                                    mean, rstd, M, D, eps));
   return 0;
 }
 
@@ -554,38 +596,36 @@ static int ln_fwd_dispatch(const float* x, const float* shift, const float* scal
 #undef LN_FWD
 }
 
-template <typename TA, int V, bool LN, bool GATE>
-static int row_bwd_launch(RowBwdParams p, int threads, cudaStream_t st) {
-  auto kernel = row_bwd_kernel<TA, V, LN, GATE>;
+template <typename TA, bool LN, bool GATE>
+static int row_bwd_dispatch(RowBwdParams p, cudaStream_t st) {
+  auto kernel = row_bwd_kernel<TA, kRowV, LN, GATE>;
+  const int D = p.D;
   const bool has_res = !LN || p.dres != nullptr;
-  const int smem = kRowStages * row_slot_bytes<TA, LN, GATE>(p.D, has_res);
-  static int configured = 0;
+  // a team = the threads of one row: kRowV float4 column groups each, whole warps (3 warps at D = 1152, 1 at D = 384)
+  const int team_threads = ceil_div(ceil_div(D / 4, kRowV), 32) * 32;
+  REED_REQUIRE(team_threads <= kRowMaxThreads, "row kernels: D = %d exceeds %d columns", D, kRowMaxThreads * kRowV * 4);
+  int teams = kRowMaxThreads / team_threads;
+  if (teams > kRowMaxTeams) teams = kRowMaxTeams;
+  // one CTA per SM (twelve elements per thread need the registers); the ring takes the shared memory: as many row slots
+  // per team as fit, at most four
+  const int slot = row_slot_bytes<TA, LN, GATE>(D, has_res);
+  int stages = (200 * 1024) / (teams * slot);
+  if (stages > kRowMaxStages) stages = kRowMaxStages;
+  while (stages < 2 && teams > 1) { --teams; stages = (200 * 1024) / (teams * slot); if (stages > kRowMaxStages) stages = kRowMaxStages; }
+  REED_REQUIRE(stages >= 1, "row kernels: a row of D = %d does not fit the shared-memory ring", D);
+  const int smem = teams * stages * slot;
+  static int configured = 0;     // per template instance
   if (configured < smem) {
     REED_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = smem;
   }
-  // one balanced wave: as many CTAs as are resident at once (shared-memory / thread bound), equal row ranges that
-  // may cross sample boundaries (the kernel flushes its column partials when the group changes)
-  int per_sm = (220 * 1024) / (smem + 1024);
-  const int by_threads = 2048 / threads;
-  if (per_sm > by_threads) per_sm = by_threads;
-  if (per_sm > 4) per_sm = 4;
-  if (per_sm < 1) per_sm = 1;
-  int rows = ceil_div(p.M, row_sm_count() * per_sm);
-  if (rows < 1) rows = 1;
+  // one balanced wave: equal row ranges that may cross sample boundaries (a team flushes its column partials when the
+  // group changes)
+  int rows = ceil_div(p.M, row_sm_count());
+  if (rows < teams) rows = teams;
   p.rows_per_cta = rows;
-  kernel<<<ceil_div(p.M, rows), threads, smem, st>>>(p);
-  REED_LAUNCH_CHECK();
+  REED_CHECK_CUDA(launch_row_kernel(kernel, ceil_div(p.M, rows), teams * team_threads, smem, st, p, team_threads, stages));
   return 0;
-}
-
-template <typename TA, bool LN, bool GATE>
-static int row_bwd_dispatch(RowBwdParams p, cudaStream_t st) {
-  const int D = p.D;
-  const int V = ceil_div(D, 4 * kRowMaxThreads);            // float4 column groups per thread (1 up to D = 1536)
-  const int threads = ceil_div(ceil_div(D / 4, V), 32) * 32;
-  if (V == 1) return row_bwd_launch<TA, 1, LN, GATE>(p, threads, st);
-  return row_bwd_launch<TA, 2, LN, GATE>(p, threads, st);
 }
 
 // ---------------------------------------------------------------------------------------------
