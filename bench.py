@@ -326,6 +326,19 @@ def run_gpu_arm(args, cfg):
             records.append((2.0 * tokens * n_out * (k_in + 1),
                             lambda: real_wgrad_bias(dy2d, x_ext, k_in, dw, db, accumulate)))
 
+    real_grouped_fwd, real_grouped_dgrad = ops.gemm_grouped_fwd, ops.gemm_grouped_dgrad
+
+    def recording_grouped_fwd(a, weights, bias_all, out):          # adaLN modulation of all blocks: one launch
+        real_grouped_fwd(a, weights, bias_all, out)
+        records.append((2.0 * a.shape[0] * out.shape[1] * a.shape[1], lambda: real_grouped_fwd(a, weights, bias_all, out)))
+        return out
+
+    def recording_grouped_dgrad(dys, weights, out, accumulate):
+        real_grouped_dgrad(dys, weights, out, accumulate)
+        records.append((2.0 * out.shape[0] * out.shape[1] * dys[0].shape[1] * len(dys),
+                        lambda: real_grouped_dgrad(dys, weights, out, accumulate)))
+        return out
+
     def eager_step(i):
         x, y, zs = resident[i % n_buf]
         trainer.train_step(x, y, zs)
@@ -333,12 +346,14 @@ def run_gpu_arm(args, cfg):
     if world > 1:
         dist.barrier()
     ops.gemm, ops.wgrad_bias = recording, recording_wgrad_bias
+    ops.gemm_grouped_fwd, ops.gemm_grouped_dgrad = recording_grouped_fwd, recording_grouped_dgrad
     tc_before = ops.tcgen05_gemm_launches()
     try:
         eager_step(0)                      # every rank runs it so the collectives stay matched
         torch.cuda.synchronize()
     finally:
         ops.gemm, ops.wgrad_bias = real_gemm, real_wgrad_bias
+        ops.gemm_grouped_fwd, ops.gemm_grouped_dgrad = real_grouped_fwd, real_grouped_dgrad
     tc_launches_in_step = ops.tcgen05_gemm_launches() - tc_before
     assert len(records) == tc_launches_in_step, (len(records), tc_launches_in_step)   # the sample is the whole population
     if rank == 0 and records:

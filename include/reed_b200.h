@@ -60,6 +60,17 @@ int reed_gemm(int act_dtype, const void* A, int64_t lda, int a_mn_major, const v
 int reed_gemm_wgrad_bias(const void* dy, int64_t ld_dy, const void* x_ext, int64_t ld_x, void* dW, int64_t ldd, void* db,
                          int n_out, int k_in, int tokens, int accumulate, void* stream);
 
+/* Several Linear layers that share their input, as ONE tensor-core launch: the adaLN-Zero modulation linears of all
+ * transformer blocks, `adaLN_modulation(c)` of models/sit.py:125-133 (28 x [6D, D] weights in separate allocations, the same
+ * silu(c) input) and the gradient of that shared input.  bf16 operands, fp32 D, M <= 128 rows, groups <= 32.
+ * A / B are HOST arrays of `groups` device pointers (mode 0 reads A[0] only); enqueue-only and graph-capturable.
+ *   mode 0: D[M, groups * per_group] = A[0][M,K] . [B_0; B_1; ...]^T + bias[groups * per_group]   (B_g [per_group, K], pitch ldb;
+ *           per_group % 256 == 0) - block g's modulation vectors are columns g * per_group ... of D.
+ *   mode 1: D[M, N] (+)= sum_g A_g[M, per_group] . B_g[per_group, N]   (K = groups * per_group, per_group % 64 == 0; split over
+ *           the reduction, fp32 atomics; `accumulate` 0 zeroes D first). */
+int reed_gemm_grouped(int mode, const void* const* A, int64_t lda, const void* const* B, int64_t ldb, int groups, int per_group,
+                      void* D, int64_t ldd, int M, int N, int K, const void* bias, int accumulate, void* stream);
+
 /* Multi-head attention, non-causal, scale head_dim^-0.5, over the packed qkv GEMM output.
  * Replaces timm Attention.forward's reshape/permute + F.scaled_dot_product_attention (models/sit.py:13,114-118,134).
  *   qkv [B,T,3,H,hd] (act dtype) -> o [B,T,H,hd] (act dtype), lse [B,H,T] fp32 (saved for backward).
@@ -91,22 +102,24 @@ int reed_ln_modulate_fwd(const void* x, const void* shift, const void* scale, in
                          void* out, int64_t ld_out, int act_dtype, void* mean, void* rstd, int M, int D, float eps,
                          void* stream);
 /* dx = dres + LN-backward(dout * (1+scale)); dshift[g] += sum dout; dscale[g] += sum dout * xhat (fp32 atomics).
- * dres may be NULL.  Replaces autograd of the above plus the residual-gradient add. */
+ * dres may be NULL.  Replaces autograd of the above plus the residual-gradient add.  ld_mod is the row pitch of the
+ * modulation vectors (scale, gate), ld_dmod that of their gradients (dshift, dscale, dgate): the two differ when the
+ * vectors of all blocks come out of one grouped GEMM (reed_gemm_grouped) while every block keeps its own gradient buffer. */
 int reed_ln_modulate_bwd(const void* dout, int act_dtype, const void* x, const void* mean, const void* rstd,
-                         const void* scale, int64_t ld_mod, int rows_per_group, const void* dres, void* dx,
+                         const void* scale, int64_t ld_mod, int64_t ld_dmod, int rows_per_group, const void* dres, void* dx,
                          void* dshift, void* dscale, int M, int D, void* stream);
 /* The two above in one pass over the rows: dx as in reed_ln_modulate_bwd, then the gate backward applied to that dx
  * (dy = gate[g] * dx, dgate[g] += sum dx * y, dbias += column sums of dy).  Used for the MLP-branch LayerNorm backward
  * followed by the attention-branch gate backward of the same block (models/sit.py:134-135): the fp32 residual gradient
- * is written once and not re-read.  gate/dgate share ld_mod with scale/dshift/dscale (views of one [B, 6D] buffer). */
+ * is written once and not re-read.  gate shares ld_mod with scale, dgate shares ld_dmod with dshift/dscale. */
 int reed_ln_modulate_gate_bwd(const void* dout, int act_dtype, const void* x, const void* mean, const void* rstd,
-                              const void* scale, int64_t ld_mod, int rows_per_group, const void* dres, void* dx,
+                              const void* scale, int64_t ld_mod, int64_t ld_dmod, int rows_per_group, const void* dres, void* dx,
                               void* dshift, void* dscale, const void* y, const void* gate, void* dy, void* dgate,
                               void* dbias, int M, int D, void* stream);
 /* Backward of x_new = x + gate[g] * y (models/sit.py:134-135): dy = gate * dxn (act dtype), dgate[g] += sum dxn * y,
  * dbias (optional, fp32 [D]) += column sums of dy. */
-int reed_gate_bwd(const void* dxn, const void* y, int act_dtype, const void* gate, int64_t ld_mod, int rows_per_group,
-                  void* dy, void* dgate, void* dbias, int M, int D, void* stream);
+int reed_gate_bwd(const void* dxn, const void* y, int act_dtype, const void* gate, int64_t ld_mod, int64_t ld_dmod,
+                  int rows_per_group, void* dy, void* dgate, void* dbias, int M, int D, void* stream);
 /* out[n] += sum_m src[m,n]  (bias gradients). */
 int reed_colsum(const void* src, int act_dtype, int64_t ld, void* out, int M, int N, void* stream);
 /* op 0: dtype cast; op 1: SiLU then cast (the SiLU in front of every adaLN linear, models/sit.py:126,149); op 2: exact

@@ -19,6 +19,8 @@ int gemm_simt(int act_dtype, const void* A, int64_t lda, int a_mn, const void* B
               int64_t ldd, int d_dtype, int M, int N, int K, const EpiParams& ep, cudaStream_t st);
 int gemm_tcgen05(const void* A, int64_t lda, int a_mn, const void* B, int64_t ldb, int b_mn, void* D, int64_t ldd,
                  int d_dtype, int M, int N, int K, const EpiParams& ep, cudaStream_t st);
+int gemm_tcgen05_grouped(int mode, const void* const* A, int64_t lda, const void* const* B, int64_t ldb, int groups, int per_group,
+                         void* D, int64_t ldd, int M, int N, int K, const EpiParams& ep, cudaStream_t st);
 bool gemm_tcgen05_supported(int64_t lda, int64_t ldb, int64_t ldd, const void* A, const void* B, int M, int N, int K);
 void gemm_tcgen05_force_cta_group(int cg);
 void gemm_tcgen05_force_bn(int bn);
@@ -108,6 +110,23 @@ extern "C" int reed_gemm(int act_dtype, const void* A, int64_t lda, int a_mn_maj
     return gemm_tcgen05(A, lda, a_mn_major, B, ldb, b_mn_major, D, ldd, d_dtype, M, N, K, ep, st);
   }
   return gemm_simt(act_dtype, A, lda, a_mn_major, B, ldb, b_mn_major, D, ldd, d_dtype, M, N, K, ep, st);
+}
+
+// Several linears that share their input as ONE tensor-core launch (the adaLN-Zero modulation linears of all blocks,
+// sit.py:125-133; bf16 operands, fp32 D, M <= 128).  A / B: host arrays of `groups` device pointers.
+//   mode 0: D[M, groups * per_group] = A[0] . [B_0; B_1; ...]^T + bias      (B_g: [per_group, K] row-major)
+//   mode 1: D[M, N] (+)= sum_g A_g[M, per_group] . B_g[per_group, N]        (the input gradient of mode 0)
+extern "C" int reed_gemm_grouped(int mode, const void* const* A, int64_t lda, const void* const* B, int64_t ldb, int groups,
+                                 int per_group, void* D, int64_t ldd, int M, int N, int K, const void* bias, int accumulate,
+                                 void* stream) {
+  REED_REQUIRE(mode == 0 || mode == 1, "gemm_grouped: mode %d", mode);
+  REED_REQUIRE(A != nullptr && B != nullptr && D != nullptr, "gemm_grouped: null operand table");
+  REED_REQUIRE(M > 0 && N > 0 && K > 0 && groups > 0 && per_group > 0, "gemm_grouped: empty problem");
+  EpiParams ep;
+  ep.kind = kEpiNone; ep.bias = (const float*)bias; ep.aux = nullptr; ep.ld_aux = 0; ep.gate = nullptr; ep.ld_gate = 0;
+  ep.rows_per_group = 1; ep.out2 = nullptr; ep.ld_out2 = 0; ep.accumulate = accumulate; ep.bias_grad = nullptr; ep.n_store = 0;
+  ++g_tcgen05_launches;
+  return gemm_tcgen05_grouped(mode, A, lda, B, ldb, groups, per_group, D, ldd, M, N, K, ep, (cudaStream_t)stream);
 }
 
 // qkv: [B, T, 3, H, hd] (act dtype); o: [B, T, H, hd]; lse: [B, H, T] fp32

@@ -184,14 +184,14 @@ struct RowBwdParams {
   const float* scale;    // LN: rows of pitch ld_mod
   const float* dres;     // LN: optional residual gradient; !LN: the incoming gradient [M,D]
   float* dx;             // LN: [M,D]
-  float* dshift;         // LN: rows of pitch ld_mod
+  float* dshift;         // LN: rows of pitch ld_dmod
   float* dscale;
   const void* y;         // GATE: [M,D] act dtype
   const float* gate;     // GATE: rows of pitch ld_mod
   void* dy;              // GATE: [M,D] act dtype
-  float* dgate;          // GATE: rows of pitch ld_mod
+  float* dgate;          // GATE: rows of pitch ld_dmod
   float* dbias;          // GATE: optional [D]
-  int64_t ld_mod;
+  int64_t ld_mod, ld_dmod;   // row pitch of the modulation vectors (scale, gate) / of their gradients
   int M, D, rows_per_group, rows_per_cta;
 };
 
@@ -299,7 +299,7 @@ __global__ void __launch_bounds__(kRowMaxThreads, 1) row_bwd_kernel(const RowBwd
 #pragma unroll
     for (int i = 0; i < V; ++i) {
       if (ok[i]) {
-        const int64_t off = (int64_t)g * p.ld_mod + col[i];
+        const int64_t off = (int64_t)g * p.ld_dmod + col[i];
         if constexpr (LN) {
           red_add_v4(p.dshift + off, a_sh[i]);
           red_add_v4(p.dscale + off, a_sc[i]);
@@ -781,46 +781,49 @@ extern "C" int reed_ln_modulate_fwd(const void* x, const void* shift, const void
 #define ROW_MOD_OK(ld) REED_REQUIRE((ld) % 4 == 0, "row kernels need modulation rows with a pitch that is a multiple of 4 floats")
 
 extern "C" int reed_ln_modulate_bwd(const void* dout, int act_dtype, const void* x, const void* mean, const void* rstd,
-                                    const void* scale, int64_t ld_mod, int rows_per_group, const void* dres, void* dx,
-                                    void* dshift, void* dscale, int M, int D, void* stream) {
+                                    const void* scale, int64_t ld_mod, int64_t ld_dmod, int rows_per_group, const void* dres,
+                                    void* dx, void* dshift, void* dscale, int M, int D, void* stream) {
   ROW_ARGS_OK(M, D, rows_per_group);
   ROW_MOD_OK(ld_mod);
+  ROW_MOD_OK(ld_dmod);
   if (M == 0) return 0;
   RowBwdParams p{};
   p.dout = dout; p.x = (const float*)x; p.mean = (const float*)mean; p.rstd = (const float*)rstd;
   p.scale = (const float*)scale; p.dres = (const float*)dres; p.dx = (float*)dx; p.dshift = (float*)dshift;
-  p.dscale = (float*)dscale; p.ld_mod = ld_mod; p.M = M; p.D = D; p.rows_per_group = rows_per_group;
+  p.dscale = (float*)dscale; p.ld_mod = ld_mod; p.ld_dmod = ld_dmod; p.M = M; p.D = D; p.rows_per_group = rows_per_group;
   cudaStream_t st = (cudaStream_t)stream;
   if (act_dtype == kBF16) return row_bwd_dispatch<bf16, true, false>(p, st);
   return row_bwd_dispatch<float, true, false>(p, st);
 }
 
 extern "C" int reed_ln_modulate_gate_bwd(const void* dout, int act_dtype, const void* x, const void* mean,
-                                         const void* rstd, const void* scale, int64_t ld_mod, int rows_per_group,
-                                         const void* dres, void* dx, void* dshift, void* dscale, const void* y,
-                                         const void* gate, void* dy, void* dgate, void* dbias, int M, int D,
+                                         const void* rstd, const void* scale, int64_t ld_mod, int64_t ld_dmod,
+                                         int rows_per_group, const void* dres, void* dx, void* dshift, void* dscale,
+                                         const void* y, const void* gate, void* dy, void* dgate, void* dbias, int M, int D,
                                          void* stream) {
   ROW_ARGS_OK(M, D, rows_per_group);
   ROW_MOD_OK(ld_mod);
+  ROW_MOD_OK(ld_dmod);
   if (M == 0) return 0;
   RowBwdParams p{};
   p.dout = dout; p.x = (const float*)x; p.mean = (const float*)mean; p.rstd = (const float*)rstd;
   p.scale = (const float*)scale; p.dres = (const float*)dres; p.dx = (float*)dx; p.dshift = (float*)dshift;
   p.dscale = (float*)dscale; p.y = y; p.gate = (const float*)gate; p.dy = dy; p.dgate = (float*)dgate;
-  p.dbias = (float*)dbias; p.ld_mod = ld_mod; p.M = M; p.D = D; p.rows_per_group = rows_per_group;
+  p.dbias = (float*)dbias; p.ld_mod = ld_mod; p.ld_dmod = ld_dmod; p.M = M; p.D = D; p.rows_per_group = rows_per_group;
   cudaStream_t st = (cudaStream_t)stream;
   if (act_dtype == kBF16) return row_bwd_dispatch<bf16, true, true>(p, st);
   return row_bwd_dispatch<float, true, true>(p, st);
 }
 
-extern "C" int reed_gate_bwd(const void* dxn, const void* y, int act_dtype, const void* gate, int64_t ld_mod,
+extern "C" int reed_gate_bwd(const void* dxn, const void* y, int act_dtype, const void* gate, int64_t ld_mod, int64_t ld_dmod,
                              int rows_per_group, void* dy, void* dgate, void* dbias, int M, int D, void* stream) {
   ROW_ARGS_OK(M, D, rows_per_group);
   ROW_MOD_OK(ld_mod);
+  ROW_MOD_OK(ld_dmod);
   if (M == 0) return 0;
   RowBwdParams p{};
   p.dres = (const float*)dxn; p.y = y; p.gate = (const float*)gate; p.dy = dy; p.dgate = (float*)dgate;
-  p.dbias = (float*)dbias; p.ld_mod = ld_mod; p.M = M; p.D = D; p.rows_per_group = rows_per_group;
+  p.dbias = (float*)dbias; p.ld_mod = ld_mod; p.ld_dmod = ld_dmod; p.M = M; p.D = D; p.rows_per_group = rows_per_group;
   cudaStream_t st = (cudaStream_t)stream;
   if (act_dtype == kBF16) return row_bwd_dispatch<bf16, false, true>(p, st);
   return row_bwd_dispatch<float, false, true>(p, st);

@@ -6,6 +6,10 @@
 namespace reed {
 
 struct EpiMaps { CUtensorMap d, o2, aux; };   // same layout as in gemm_tcgen05.cuh
+constexpr int kMaxGroups = 32;
+struct GroupMaps { CUtensorMap a[kMaxGroups], b[kMaxGroups]; int mode, per_group; };   // same layout as in gemm_tcgen05.cuh
+int gemm_tc_launch_grouped(int bn, int b_mn, const GroupMaps& gm, void* D, int64_t ldd, int M, int N, int K, const EpiParams& ep,
+                           cudaStream_t st, int grid, int stream_k);
 
 int gemm_tc_launch_cg1(int bn, int a_mn, int b_mn, const CUtensorMap& ma, const CUtensorMap& mb, void* D, int64_t ldd,
                        int d_dtype, int M, int N, int K, const EpiParams& ep, cudaStream_t st, int grid, int stream_k,
@@ -219,6 +223,43 @@ int gemm_tcgen05(const void* A, int64_t lda, int a_mn, const void* B, int64_t ld
   }
   if (p.cg == 2) return gemm_tc_launch_cg2(p.bn, a_mn, b_mn, ma, mb, D, ldd, d_dtype, M, N, K, ep, st, p.grid, p.stream_k, emp);
   return gemm_tc_launch_cg1(p.bn, a_mn, b_mn, ma, mb, D, ldd, d_dtype, M, N, K, ep, st, p.grid, p.stream_k, emp);
+}
+
+// Grouped operands (see GroupMaps in gemm_tcgen05.cuh).  A: [M, K] K-major bf16, M <= 128 (one row tile).
+//   mode 0: D[M, groups * n_per_group] = A . [B_0; B_1; ...]^T + bias, B_g [n_per_group, K] K-major (separate allocations)
+//   mode 1: D[M, N] (+)= sum_g A_g[M, k_per_group] . B_g[k_per_group, N], B_g MN-major; split over k, fp32 atomics
+int gemm_tcgen05_grouped(int mode, const void* const* A, int64_t lda, const void* const* B, int64_t ldb, int groups, int per_group,
+                         void* D, int64_t ldd, int M, int N, int K, const EpiParams& ep, cudaStream_t st) {
+  REED_REQUIRE(groups >= 1 && groups <= kMaxGroups, "gemm_grouped: %d groups (1..%d)", groups, kMaxGroups);
+  REED_REQUIRE(M >= 1 && M <= 128, "gemm_grouped: M = %d (a single row tile, <= 128)", M);
+  REED_REQUIRE(lda % 8 == 0 && ldb % 8 == 0 && ldd % 4 == 0, "gemm_grouped: row pitches must keep 16-byte alignment");
+  REED_REQUIRE(ep.kind == kEpiNone && ep.out2 == nullptr && ep.bias_grad == nullptr, "gemm_grouped: plain fp32 output only");
+  GroupMaps gm;             // ~8 KB, copied into the launch
+  gm.mode = mode;
+  GemmPlan p;
+  if (mode == 0) {
+    REED_REQUIRE(N == groups * per_group && per_group % 256 == 0, "gemm_grouped: N = groups x n_per_group, n_per_group %% 256 == 0");
+    REED_REQUIRE(!ep.accumulate, "gemm_grouped: the forward form overwrites D");
+    gm.per_group = per_group;
+    p = plan_gemm(M, N, K, 0, false, 1, 256);
+    if (make_map(&gm.a[0], A[0], M, K, lda, 128)) return 1;
+    for (int g = 0; g < groups; ++g) {
+      REED_REQUIRE(((uintptr_t)B[g] & 15) == 0, "gemm_grouped: operand %d is not 16-byte aligned", g);
+      if (make_map(&gm.b[g], B[g], per_group, K, ldb, p.bn)) return 1;
+    }
+  } else {
+    REED_REQUIRE(K == groups * per_group && per_group % 64 == 0, "gemm_grouped: K = groups x k_per_group, k_per_group %% 64 == 0");
+    REED_REQUIRE(N % 8 == 0, "gemm_grouped: N %% 8 == 0");
+    gm.per_group = per_group / 64;          // in k-blocks
+    p = plan_gemm(M, N, K, 1, ep.bias == nullptr, 1, 256);
+    if (p.stream_k > 1 && !ep.accumulate) REED_CHECK_CUDA(cudaMemset2DAsync(D, (size_t)ldd * 4, 0, (size_t)N * 4, (size_t)M, st));
+    for (int g = 0; g < groups; ++g) {
+      REED_REQUIRE((((uintptr_t)A[g] | (uintptr_t)B[g]) & 15) == 0, "gemm_grouped: operand %d is not 16-byte aligned", g);
+      if (make_map(&gm.a[g], A[g], M, per_group, lda, 128)) return 1;
+      if (make_map(&gm.b[g], B[g], per_group, N, ldb, 64)) return 1;
+    }
+  }
+  return gemm_tc_launch_grouped(p.bn, mode, gm, D, ldd, M, N, K, ep, st, p.grid, p.stream_k);
 }
 
 }  // namespace reed

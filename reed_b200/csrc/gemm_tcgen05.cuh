@@ -61,6 +61,17 @@ struct GemmCfg {
 // (one epilogue warp's share of a chunk) with the 64-byte (bf16) / 128-byte (fp32) swizzle.
 struct EpiMaps { CUtensorMap d, o2, aux; };
 
+// Grouped operands (the adaLN-Zero modulation linears of ALL blocks as one launch, sit.py:125-133): up to kMaxGroups
+// weight matrices that live in separate allocations, presented to the kernel as one virtual operand.
+//   mode 0 (forward, mod_g = c W_g^T): the virtual B is the groups' [n_per_group, K] matrices stacked along N; a column
+//           tile lies in one group (n_per_group % BN == 0) and the producer picks that group's tensor map.
+//   mode 1 (dgrad, dc = sum_g dmod_g W_g): the groups are concatenated along the reduction; k-block kb belongs to group
+//           kb / kb_per_group and both operands come from that group's maps.
+// The maps travel as a kernel parameter (__grid_constant__, ~8 KB), so the call is capturable in a CUDA graph.
+constexpr int kMaxGroups = 32;
+struct GroupMaps { CUtensorMap a[kMaxGroups], b[kMaxGroups]; int mode, per_group; };
+struct NoGroups { int unused; };
+
 // Work distribution.  Data-parallel: output tiles round-robin over the persistent CTAs (pairs), rounds in lock step,
 // so the CTAs running at any moment read the same k range of neighbouring tiles and L2 serves each operand line to
 // several SMs at once.  Split mode (fp32 outputs that tolerate atomics, i.e. the weight-gradient GEMMs, whose tile
@@ -629,11 +640,13 @@ __device__ __forceinline__ void epilogue_loop_tma_gateres(const EpiParams& ep, c
   __syncwarp();
 }
 
-template <int CG, int BN, int A_MN, int B_MN, typename TD>
+template <int CG, int BN, int A_MN, int B_MN, typename TD, typename GM = NoGroups>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                     const __grid_constant__ EpiMaps emaps, TD* __restrict__ D, int64_t ldd, int M, int N, int K,
-                    EpiParams ep, int stream_k, int dbg, int stages, int epi_bytes, int tma_epi) {
+                    EpiParams ep, int stream_k, int dbg, int stages, int epi_bytes, int tma_epi,
+                    const __grid_constant__ GM gmaps) {
+  constexpr bool kGrouped = sizeof(GM) > sizeof(NoGroups);
   // stages / epi_bytes: pipeline depth and size of the epilogue's shared-memory region (host: GemmCfg::stages_for);
   // tma_epi: 0 = register / LSU epilogue; 1 = TMA epilogue (epilogue_loop_tma; emaps valid); fp32 D (gate+residual):
   // the number of residual ring slots per warp (epilogue_loop_tma_gateres)
@@ -716,29 +729,47 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     while (!(dbg & 1) && sched.next(sg)) {
       const int m0 = (sg.tile / tiles_n) * BMT + (int)rank * BM;
       // a half tile is BN/2 wide: each CTA of the pair supplies BN/2/CG rows of B, taken from the head of its box
-      const int n0 = (sg.tile % tiles_n) * BN + (int)rank * (sg.half ? BNL / 2 : BNL);
+      int n0 = (sg.tile % tiles_n) * BN + (int)rank * (sg.half ? BNL / 2 : BNL);
+      const CUtensorMap* pa = &map_a;
+      const CUtensorMap* pb = &map_b;
+      if constexpr (kGrouped) {
+        if (gmaps.mode == 0) {                 // the column tile's group supplies B
+          const int g = n0 / gmaps.per_group;
+          n0 -= g * gmaps.per_group;
+          pb = &gmaps.b[g];
+        }
+      }
       for (int kb = sg.kb0; kb < sg.kb1; ++kb) {
         mbar_wait(&empty[stage], phase ^ 1);
         const uint32_t sa = stage0 + stage * Cfg::kStageBytes;
         const uint32_t sb = sa + Cfg::kABytes;
         const uint32_t fbar = full0 + stage * 8;
-        const int k0 = kb * BK;
+        int k0 = kb * BK;
+        if constexpr (kGrouped) {
+          if (gmaps.mode == 1) {               // the k-block's group supplies both operands
+            const int g = kb / gmaps.per_group;
+            k0 = (kb - g * gmaps.per_group) * BK;
+            pa = &gmaps.a[g];
+            pb = &gmaps.b[g];
+          }
+        }
         if (issuer) {
           if constexpr (CG == 1) {
             mbar_expect_tx_u32(fbar, Cfg::kStageBytes);
             if (A_MN) {
 #pragma unroll
-              for (int c = 0; c < BM / 64; ++c) tma_load_2d_u32(&map_a, fbar, sa + c * (BK * 128), m0 + c * 64, k0);
+              for (int c = 0; c < BM / 64; ++c) tma_load_2d_u32(pa, fbar, sa + c * (BK * 128), m0 + c * 64, k0);
             } else {
-              tma_load_2d_u32(&map_a, fbar, sa, k0, m0);
+              tma_load_2d_u32(pa, fbar, sa, k0, m0);
             }
             if (B_MN) {
 #pragma unroll
-              for (int c = 0; c < BNL / 64; ++c) tma_load_2d_u32(&map_b, fbar, sb + c * (BK * 128), n0 + c * 64, k0);
+              for (int c = 0; c < BNL / 64; ++c) tma_load_2d_u32(pb, fbar, sb + c * (BK * 128), n0 + c * 64, k0);
             } else {
-              tma_load_2d_u32(&map_b, fbar, sb, k0, n0);
+              tma_load_2d_u32(pb, fbar, sb, k0, n0);
             }
           } else {
+            static_assert(!kGrouped || CG == 1, "grouped operands: cta_group::1 kernels only");
             if (leader) mbar_expect_tx_u32(fbar, CG * Cfg::kStageBytes);
             const uint32_t fb = mapa_u32(fbar, 0);
             if (A_MN) {
@@ -887,9 +918,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
 // ------------------------------------------------------------------------------------------------
 // launch helpers (instantiated in gemm_tcgen05_cg1.cu / gemm_tcgen05_cg2.cu)
 // ------------------------------------------------------------------------------------------------
-template <int CG, int BN, int A_MN, int B_MN, typename TD>
+template <int CG, int BN, int A_MN, int B_MN, typename TD, typename GM = NoGroups>
 static int launch(const CUtensorMap& ma, const CUtensorMap& mb, void* D, int64_t ldd, int M, int N, int K,
-                  const EpiParams& ep, cudaStream_t st, int grid, int stream_k, const EpiMaps* em) {
+                  const EpiParams& ep, cudaStream_t st, int grid, int stream_k, const EpiMaps* em, const GM* gm = nullptr) {
   static const int dbg = getenv("REED_GEMM_DEBUG") ? atoi(getenv("REED_GEMM_DEBUG")) : 0;
   using Cfg = GemmCfg<CG, BN>;
   static_assert(Cfg::stages_for(Cfg::kStagingBytes) >= 3, "pipeline too shallow");
@@ -916,7 +947,7 @@ static int launch(const CUtensorMap& ma, const CUtensorMap& mb, void* D, int64_t
   static const int max_stages = getenv("REED_GEMM_MAX_STAGES") ? atoi(getenv("REED_GEMM_MAX_STAGES")) : 8;   // profiling knob
   const int stages = Cfg::stages_for(epi_bytes) < max_stages ? Cfg::stages_for(epi_bytes) : (max_stages < 2 ? 2 : max_stages);
   const int smem = Cfg::smem_bytes(stages, epi_bytes);
-  auto kernel = gemm_tcgen05_kernel<CG, BN, A_MN, B_MN, TD>;
+  auto kernel = gemm_tcgen05_kernel<CG, BN, A_MN, B_MN, TD, GM>;
   static bool configured = false;   // per template instance
   if (!configured) {
     REED_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -938,8 +969,9 @@ static int launch(const CUtensorMap& ma, const CUtensorMap& mb, void* D, int64_t
   cfg.attrs = attr;
   cfg.numAttrs = pdl ? 2 : 1;
   static const EpiMaps no_maps{};
+  static const GM no_groups{};
   REED_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kernel, ma, mb, tma_epi ? *em : no_maps, (TD*)D, ldd, M, N, K, ep, stream_k, dbg,
-                                     stages, epi_bytes, tma_epi));
+                                     stages, epi_bytes, tma_epi, gm != nullptr ? *gm : no_groups));
   return 0;
 }
 

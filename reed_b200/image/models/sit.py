@@ -139,16 +139,17 @@ class SiTBlock(nn.Module):
         self.mlp = _MlpParams(hidden_size, int(hidden_size * mlp_ratio))
         self.adaLN_modulation = nn.Sequential(nn.SiLU(), nn.Linear(hidden_size, 6 * hidden_size, bias=True))
 
-    def forward(self, x, c_act, act_dtype, c_acc=None):
+    def forward(self, x, c_act, act_dtype, c_acc=None, ada=None):
         """x: (N,T,D) fp32; c_act = silu(c) already in the act dtype (shared by every block); c_acc: the side
-        accumulator the block adds its gradient w.r.t. c_act into (ops.silu_cast)."""
+        accumulator the block adds its gradient w.r.t. c_act into (ops.silu_cast); ada: (ops.AdaLNAll, block index) when
+        the modulation vectors of all blocks were computed by one grouped GEMM."""
         lin = self.adaLN_modulation[1]
         a, m = self.attn, self.mlp
         return ops.SiTBlockFn.apply(x, c_act, lin.weight, lin.bias, a.qkv.weight, a.qkv.bias, a.proj.weight, a.proj.bias,
                                     m.fc1.weight, m.fc1.bias, m.fc2.weight, m.fc2.bias, self.num_heads, act_dtype,
                                     getattr(self, "_reed_after_backward", None), c_acc,
                                     *((a.q_norm.weight, a.q_norm.bias, a.k_norm.weight, a.k_norm.bias) if self.qk_norm
-                                      else ()))
+                                      else (None, None, None, None)), ada)
 
 
 class FinalLayer(nn.Module):
@@ -272,8 +273,11 @@ class SiT(nn.Module):
         split = self.encoder_depth_text is not None and self.encoder_depth_text != self.encoder_depth
         zs = None
         z_img = z_txt = None
+        # adaLN_modulation(c) of all blocks in one grouped GEMM (the weights stay separate parameters)
+        ada_lin = [blk.adaLN_modulation[1] for blk in self.blocks]
+        ada_all = ops.AdaLNAll(c_act, ada_lin, act_dtype, c_acc) if ops.AdaLNAll.usable(c_act, ada_lin, act_dtype) else None
         for i, blk in enumerate(self.blocks, start=1):
-            tok = blk(tok, c_act, act_dtype, c_acc)
+            tok = blk(tok, c_act, act_dtype, c_acc, (ada_all, i - 1) if ada_all is not None else None)
             if inference:
                 continue
             if i == self.encoder_depth:

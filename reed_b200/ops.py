@@ -31,6 +31,9 @@ _WGRAD_BIAS = _os.environ.get("REED_WGRAD_BIAS", "1") != "0"
 # (N = 1152 shapes run 160 tiles on 74 CTA pairs: the third round is 16 % full).  Measured on the B200 in round 2:
 # 909 -> 927 img/s on the XL/2 step (profiles/r02_bench_flags.txt); REED_WGRAD_STREAM=0 restores the single stream for A/B.
 _WGRAD_STREAM = _os.environ.get("REED_WGRAD_STREAM", "1") != "0"
+# The adaLN modulation linears of all blocks as one grouped GEMM (AdaLNAll); REED_ADALN_GROUPED=0 restores one GEMM per
+# block for A/B runs.
+_ADALN_GROUPED = _os.environ.get("REED_ADALN_GROUPED", "1") != "0"
 _gemm_backend = BACKEND_AUTO
 _attn_backend = BACKEND_AUTO
 launch_count = 0     # kernels launched through this module (bench.py reports it as gpu_launches)
@@ -204,13 +207,45 @@ def wgrad_bias(dy2d, x_ext, k_in, dw, db, accumulate):
             n_out, k_in, tokens, int(accumulate), _stream())
 
 
+def _ptr_table(tensors):
+    import ctypes
+    return (ctypes.c_void_p * len(tensors))(*[t.data_ptr() for t in tensors])
+
+
+def gemm_grouped_fwd(a, weights, bias_all, out):
+    """out[M, G*n] = a . [W_0; W_1; ...]^T + bias_all in one tensor-core launch (reed_gemm_grouped mode 0): G linears with
+    separately stored [n, K] weights applied to the same bf16 input (the adaLN modulation of every block)."""
+    M, K = a.shape
+    n = weights[0].shape[0]
+    assert a.dtype == torch.bfloat16 and a.stride(1) == 1 and out.dtype == torch.float32 and out.stride(1) == 1
+    assert all(w.dtype == torch.bfloat16 and w.shape == (n, K) and w.stride(1) == 1 and w.stride(0) == weights[0].stride(0)
+               for w in weights)
+    assert out.shape == (M, n * len(weights)) and bias_all.numel() == n * len(weights) and bias_all.dtype == torch.float32
+    _launch("reed_gemm_grouped", 0, _ptr_table([a]), a.stride(0), _ptr_table(weights), weights[0].stride(0), len(weights), n,
+            _p(out), out.stride(0), M, n * len(weights), K, _p(bias_all), 0, _stream())
+    return out
+
+
+def gemm_grouped_dgrad(dys, weights, out, accumulate):
+    """out[M, K] (+)= sum_g dy_g[M, n] . W_g[n, K]  (reed_gemm_grouped mode 1): the gradient of the shared input of G linears."""
+    M, n = dys[0].shape
+    K = weights[0].shape[1]
+    assert all(d.dtype == torch.bfloat16 and d.shape == (M, n) and d.stride(1) == 1 and d.stride(0) == dys[0].stride(0) for d in dys)
+    assert all(w.dtype == torch.bfloat16 and w.shape == (n, K) and w.stride(1) == 1 and w.stride(0) == weights[0].stride(0)
+               for w in weights)
+    assert out.shape == (M, K) and out.dtype == torch.float32 and out.stride(1) == 1 and len(dys) == len(weights)
+    _launch("reed_gemm_grouped", 1, _ptr_table(dys), dys[0].stride(0), _ptr_table(weights), weights[0].stride(0), len(weights), n,
+            _p(out), out.stride(0), M, K, n * len(weights), None, int(accumulate), _stream())
+    return out
+
+
 def ln_modulate_bwd(dout, x, mean, rstd, scale, rows_per_group, dres, dshift, dscale):
-    """Returns dx = dres + LN'(dout); accumulates into dshift/dscale (views with the same row stride as scale)."""
+    """Returns dx = dres + LN'(dout); accumulates into dshift/dscale (two views with one row stride)."""
     M, D = x.shape
     dx = torch.empty_like(x)
-    assert dshift.stride(0) == scale.stride(0) == dscale.stride(0)
+    assert dshift.stride(0) == dscale.stride(0)
     _launch("reed_ln_modulate_bwd", _p(dout), _code(dout.dtype), _p(x), _p(mean), _p(rstd), _p(scale), scale.stride(0),
-            rows_per_group, _p(dres), _p(dx), _p(dshift), _p(dscale), M, D, _stream())
+            dshift.stride(0), rows_per_group, _p(dres), _p(dx), _p(dshift), _p(dscale), M, D, _stream())
     return dx
 
 
@@ -220,9 +255,9 @@ def ln_modulate_gate_bwd(dout, x, mean, rstd, scale, rows_per_group, dres, dshif
     dx = torch.empty_like(x)
     dy = torch.empty_like(y)
     ld = scale.stride(0)
-    assert dshift.stride(0) == ld == dscale.stride(0) == gate.stride(0) == dgate.stride(0)
+    assert ld == gate.stride(0) and dshift.stride(0) == dscale.stride(0) == dgate.stride(0)
     _launch("reed_ln_modulate_gate_bwd", _p(dout), _code(dout.dtype), _p(x), _p(mean), _p(rstd), _p(scale), ld,
-            rows_per_group, _p(dres), _p(dx), _p(dshift), _p(dscale), _p(y), _p(gate), _p(dy), _p(dgate), _p(dbias), M, D,
+            dshift.stride(0), rows_per_group, _p(dres), _p(dx), _p(dshift), _p(dscale), _p(y), _p(gate), _p(dy), _p(dgate), _p(dbias), M, D,
             _stream())
     return dx, dy
 
@@ -230,8 +265,8 @@ def ln_modulate_gate_bwd(dout, x, mean, rstd, scale, rows_per_group, dres, dshif
 def gate_bwd(dxn, y, gate, rows_per_group, dgate, dbias):
     M, D = dxn.shape
     dy = torch.empty_like(y)
-    assert dgate.stride(0) == gate.stride(0)
-    _launch("reed_gate_bwd", _p(dxn), _p(y), _code(y.dtype), _p(gate), gate.stride(0), rows_per_group, _p(dy), _p(dgate),
+    _launch("reed_gate_bwd", _p(dxn), _p(y), _code(y.dtype), _p(gate), gate.stride(0), dgate.stride(0), rows_per_group, _p(dy),
+            _p(dgate),
             _p(dbias), M, D, _stream())
     return dy
 
@@ -403,15 +438,59 @@ def linear(x, weight, bias, *, act=ACT_NONE, act_dtype, out_dtype=None):
 
 class _GradAccumulator:
     """fp32 side buffer the consumers of a shared tensor add their input gradients into (one split-K GEMM each),
-    instead of handing autograd 28 separate bf16 gradients to sum."""
+    instead of handing autograd 28 separate bf16 gradients to sum.  `deferred`: work to run right before the buffer is
+    read (the grouped input gradient of the blocks' modulation linears, AdaLNAll)."""
 
     def __init__(self):
         self.buf = None
+        self.deferred = []
 
     def get(self, like, dtype=torch.float32):
         if self.buf is None:
             self.buf = torch.zeros(like.shape, device=like.device, dtype=dtype)
         return self.buf
+
+
+ADALN_GROUP_MAX = 32       # kMaxGroups of reed_gemm_grouped
+
+
+class AdaLNAll:
+    """adaLN_modulation(c) of EVERY transformer block (sit.py:125-133) as one grouped GEMM: the blocks' [6D, D] weights are
+    separate parameters, silu(c) is shared.  forward: mod_all[B, L*6D] = c_act [W_0; ...; W_{L-1}]^T + [b_0; ...]; block i reads
+    columns i*6D..(i+1)*6D.  backward: every block leaves its dmod (act dtype) in `dmods[i]` and computes its own weight / bias
+    gradients; the input gradient sum_i dmod_i W_i is one more grouped GEMM, run when the gradient of silu(c) is collected
+    (SiluCastFn.backward).  Per block this replaces a 54-CTA forward GEMM (14 us for a 16 MB weight stream) and a split-K
+    dgrad GEMM (12 us) by 1/28 of two launches that stream the 446 MB of weights at HBM speed."""
+
+    def __init__(self, c_act, linears, act_dtype, c_acc):
+        self.c_act = c_act
+        self.weights = [weight_for(l.weight, act_dtype) for l in linears]
+        self.width = linears[0].weight.shape[0]
+        bias_all = torch.cat([l.bias.detach() for l in linears])
+        self.mod_all = torch.empty((c_act.shape[0], self.width * len(linears)), device=c_act.device, dtype=torch.float32)
+        gemm_grouped_fwd(c_act, self.weights, bias_all, self.mod_all)
+        self.dmods = [None] * len(linears)
+        self.c_acc = c_acc
+        if c_acc is not None:
+            c_acc.deferred.append(self._input_grad)
+
+    @staticmethod
+    def usable(c_act, linears, act_dtype):
+        w = linears[0].weight
+        return (act_dtype == torch.bfloat16 and c_act.dtype == torch.bfloat16 and 1 <= len(linears) <= ADALN_GROUP_MAX
+                and c_act.shape[0] <= 128 and w.shape[0] % 256 == 0 and w.shape[1] % 8 == 0 and w.shape[1] >= 64
+                and _ADALN_GROUPED and (_gemm_backend & 7) != BACKEND_SIMT
+                and all(l.weight.shape == w.shape and l.bias is not None for l in linears))
+
+    def mod(self, i):
+        return self.mod_all[:, i * self.width:(i + 1) * self.width]
+
+    def _input_grad(self):
+        done = [i for i, d in enumerate(self.dmods) if d is not None]
+        if not done:
+            return
+        gemm_grouped_dgrad([self.dmods[i] for i in done], [self.weights[i] for i in done], self.c_acc.get(self.c_act), True)
+        self.dmods = [None] * len(self.dmods)
 
 
 class SiluCastFn(torch.autograd.Function):
@@ -429,6 +508,9 @@ class SiluCastFn(torch.autograd.Function):
     def backward(ctx, dy):
         (c,) = ctx.saved_tensors
         dy = cast(dy.contiguous(), torch.float32)
+        for fn in ctx.acc.deferred:          # the blocks' grouped adaLN input gradient lands in the side buffer
+            fn()
+        ctx.acc.deferred = []
         if ctx.acc.buf is not None:          # gradients the transformer blocks accumulated on the side
             total = torch.empty_like(dy)
             _launch("reed_add_f32", _p(dy), _p(ctx.acc.buf), _p(total), dy.numel(), _stream())
@@ -502,7 +584,7 @@ class SiTBlockFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, c_act, w_ada, b_ada, w_qkv, b_qkv, w_proj, b_proj, w_fc1, b_fc1, w_fc2, b_fc2, num_heads,
-                act_dtype, after_backward, c_acc=None, qn_w=None, qn_b=None, kn_w=None, kn_b=None):
+                act_dtype, after_backward, c_acc=None, qn_w=None, qn_b=None, kn_w=None, kn_b=None, ada=None):
         _require_cuda(x, c_act)
         B, T, D = x.shape
         M = B * T
@@ -511,7 +593,8 @@ class SiTBlockFn(torch.autograd.Function):
         c_act = c_act.contiguous()
         W = lambda p: weight_for(p, act_dtype)
 
-        mod = gemm(c_act, W(w_ada), out_dtype=torch.float32, bias=b_ada.detach())
+        # ada = (AdaLNAll, block index): the modulation vectors of every block came out of one grouped GEMM
+        mod = ada[0].mod(ada[1]) if ada is not None else gemm(c_act, W(w_ada), out_dtype=torch.float32, bias=b_ada.detach())
         sh_a, sc_a, g_a, sh_m, sc_m, g_m = (mod[:, i * D:(i + 1) * D] for i in range(6))
         xm1, mean1, rstd1 = ln_modulate_fwd(x0, sh_a, sc_a, T, act_dtype, ones_col=True)
         qkv_raw = gemm(xm1, W(w_qkv), out_dtype=act_dtype, bias=b_qkv.detach())
@@ -541,6 +624,7 @@ class SiTBlockFn(torch.autograd.Function):
         ctx.act_dtype = act_dtype
         ctx.after_backward = after_backward
         ctx.c_acc = c_acc
+        ctx.ada = ada
         return x2.view(B, T, D)
 
     @staticmethod
@@ -609,7 +693,9 @@ class SiTBlockFn(torch.autograd.Function):
         db_ada = _bias_grad(b_ada, dmod)
         dw_ada = off_stream(lambda: _weight_grad(w_ada, dmod_a, c_act), dmod_a, c_act)
         dc = None
-        if ctx.needs_input_grad[1]:
+        if ctx.ada is not None and ctx.ada[0].c_acc is not None:
+            ctx.ada[0].dmods[ctx.ada[1]] = dmod_a      # its share of dL/d silu(c): one grouped GEMM for all blocks, later
+        elif ctx.needs_input_grad[1]:
             if ctx.c_acc is not None:     # [B, 6D] x [6D, D]: few rows, long reduction -> split-K slices add into the side buffer
                 gemm(dmod_a, W(w_ada), b_mn=True, out=ctx.c_acc.get(c_act), accumulate=True)
             else:
@@ -619,7 +705,7 @@ class SiTBlockFn(torch.autograd.Function):
             side.join()                       # the bucket's gradients are complete on the current stream from here on
         if ctx.after_backward is not None:
             ctx.after_backward()
-        return (dx0.view(B, T, D), dc, dw_ada, db_ada, dwqkv, dbqkv, dwp, dbp, dw1, db1, dw2, db2, None, None, None, None) + qk_grads
+        return (dx0.view(B, T, D), dc, dw_ada, db_ada, dwqkv, dbqkv, dwp, dbp, dw1, db1, dw2, db2, None, None, None, None) + qk_grads + (None,)
 
 
 # --------------------------------------------------------------------------------------------------

@@ -154,6 +154,28 @@ def test_gemm_tma_epilogue_many_tiles(ops, bn):
     assert _rel(got.float(), want) < 1.5e-2
 
 
+@pytest.mark.parametrize("shape", [(32, 1152, 28), (4, 128, 2), (128, 384, 5), (7, 768, 12)])      # (batch, width, blocks)
+def test_gemm_grouped_adaln(ops, shape):
+    """reed_gemm_grouped: adaLN_modulation(c) of all blocks (sit.py:125-133) as one launch over separately stored weights,
+    and the gradient of the shared input as one split-K launch over the concatenated reduction."""
+    B, D, L = shape
+    c = _rand(B, D, dtype=torch.bfloat16, seed=1)
+    ws = [_rand(6 * D, D, dtype=torch.bfloat16, scale=D ** -0.5, seed=10 + g) for g in range(L)]
+    bias = _rand(L * 6 * D, seed=2)
+    out = torch.empty(B, L * 6 * D, device=DEV)
+    ops.gemm_grouped_fwd(c, ws, bias, out)
+    want = torch.cat([c.float() @ w.float().t() for w in ws], dim=1) + bias
+    assert _rel(out, want) < 2e-3
+    dys = [_rand(B, 6 * D, dtype=torch.bfloat16, seed=50 + g) for g in range(L)]
+    want = sum(d.float() @ w.float() for d, w in zip(dys, ws))
+    dc = torch.full((B, D), 7.0, device=DEV)
+    ops.gemm_grouped_dgrad(dys, ws, dc, accumulate=False)
+    assert _rel(dc, want) < 2e-3
+    ops.gemm_grouped_dgrad(dys[:max(1, L // 2)], ws[:max(1, L // 2)], dc, accumulate=True)
+    want2 = want + sum(d.float() @ w.float() for d, w in zip(dys[:max(1, L // 2)], ws[:max(1, L // 2)]))
+    assert _rel(dc, want2) < 2e-3
+
+
 @pytest.mark.parametrize("bn", [0, 1, 2, 3])                   # planner's choice / tile width 128 / 192 / 256
 @pytest.mark.parametrize("cg", [1, 2])
 def test_gemm_gate_residual_many_tiles(ops, bn, cg):

@@ -347,3 +347,36 @@ def test_full_size_properties_xl2_bf16():
         p2, _ = model(x[perm], tt[perm], y=y[perm])
     assert torch.isfinite(p1).all()
     assert float((p1[perm] - p2).abs().max()) < 1e-5 * max(1.0, float(p1.abs().max()))
+
+
+def test_grouped_adaln_matches_per_block_gemms():
+    """adaLN_modulation(c) of all blocks as one grouped GEMM + one grouped input-gradient GEMM (ops.AdaLNAll) against the
+    per-block GEMMs it replaces (sit.py:125-133): same predictions, same gradients for every parameter upstream of c."""
+    from reed_b200 import ops
+    spec = ArchSpec(input_size=16, hidden_size=128, decoder_hidden_size=128, depth=5, num_heads=2, encoder_depth=2,
+                    z_dims=[64], z_types=["i"], projector_dim=128, num_classes=10)
+    sd = random_state(spec, 3)
+    data = random_batch(spec, 6, 4)
+    x, y = data["x"].to(DEV), data["y"].to(DEV)
+    t = torch.linspace(0.1, 0.9, 6, device=DEV)
+    results = []
+    for grouped in (True, False):
+        old = ops._ADALN_GROUPED
+        ops._ADALN_GROUPED = grouped
+        try:
+            model = _build(spec, sd, "bf16").eval()
+            launches = ops.launch_count
+            pred, _ = model(x, t, y, inference=False)
+            (pred.float() ** 2).mean().backward()
+            results.append((pred.detach().float(), {n: p.grad.detach().float().clone() for n, p in model.named_parameters()
+                                                    if p.grad is not None}, ops.launch_count - launches))
+        finally:
+            ops._ADALN_GROUPED = old
+    (p_g, g_g, n_g), (p_b, g_b, n_b) = results
+    assert n_g < n_b                                     # the grouped path really ran (fewer launches)
+    assert _rel(p_g, p_b) < 2e-3
+    for name in g_b:
+        cos = F.cosine_similarity(g_g[name].flatten(), g_b[name].flatten(), dim=0)
+        assert float(cos) > 0.9999, (name, float(cos))
+    for name in ("t_embedder.mlp.0.weight", "y_embedder.embedding_table.weight"):
+        assert _rel(g_g[name], g_b[name]) < 1e-2, name
