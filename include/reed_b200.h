@@ -60,6 +60,13 @@ int reed_gemm(int act_dtype, const void* A, int64_t lda, int a_mn_major, const v
 int reed_gemm_wgrad_bias(const void* dy, int64_t ld_dy, const void* x_ext, int64_t ld_x, void* dW, int64_t ldd, void* db,
                          int n_out, int k_in, int tokens, int accumulate, void* stream);
 
+/* Weight and bias gradient of a Linear whose contraction is the batch (rows <= 64): autograd of `adaLN_modulation` and the
+ * timestep-embedder linears (models/sit.py:125-128, 40-44) - an outer-product stream bounded by the write of dW.
+ *   dW[n_out, k_in] (+)= dy^T x;  db[n_out] += column sums of dy (NULL to skip; the caller zeroes it once per step).
+ *   dy [rows, n_out] (fp32 or bf16, pitch ld_dy), x [rows, k_in] (bf16, or fp32 with fp32 dy; pitch ld_x). */
+int reed_outer_wgrad(const void* dy, int dy_dtype, int64_t ld_dy, const void* x, int x_dtype, int64_t ld_x, void* dW, int64_t ldd,
+                     void* db, int n_out, int k_in, int rows, int accumulate, void* stream);
+
 /* Several Linear layers that share their input, as ONE tensor-core launch: the adaLN-Zero modulation linears of all
  * transformer blocks, `adaLN_modulation(c)` of models/sit.py:125-133 (28 x [6D, D] weights in separate allocations, the same
  * silu(c) input) and the gradient of that shared input.  bf16 operands, fp32 D, M <= 128 rows, groups <= 32.

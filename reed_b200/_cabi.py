@@ -27,6 +27,7 @@ _SIGNATURES = {
     "reed_ln_modulate_fwd": [P, P, P, L, I, P, L, I, P, P, I, I, F, P],
     "reed_gemm_wgrad_bias": [P, L, P, L, P, L, P, I, I, I, I, P],
     "reed_gemm_grouped": [I, P, L, P, L, I, I, P, L, I, I, I, P, I, P],
+    "reed_outer_wgrad": [P, I, L, P, I, L, P, L, P, I, I, I, I, P],
     "reed_ln_modulate_bwd": [P, I, P, P, P, P, L, L, I, P, P, P, P, I, I, P],
     "reed_ln_modulate_gate_bwd": [P, I, P, P, P, P, L, L, I, P, P, P, P, P, P, P, P, P, I, I, P],
     "reed_gate_bwd": [P, P, I, P, L, L, I, P, P, P, I, I, P],

@@ -19,6 +19,8 @@ int gemm_simt(int act_dtype, const void* A, int64_t lda, int a_mn, const void* B
               int64_t ldd, int d_dtype, int M, int N, int K, const EpiParams& ep, cudaStream_t st);
 int gemm_tcgen05(const void* A, int64_t lda, int a_mn, const void* B, int64_t ldb, int b_mn, void* D, int64_t ldd,
                  int d_dtype, int M, int N, int K, const EpiParams& ep, cudaStream_t st);
+int outer_wgrad(int dy_dtype, const void* dy, int64_t ld_dy, int x_dtype, const void* x, int64_t ld_x, float* D, int64_t ldd,
+                int N, int K, int B, int accumulate, float* db, cudaStream_t st);
 int gemm_tcgen05_grouped(int mode, const void* const* A, int64_t lda, const void* const* B, int64_t ldb, int groups, int per_group,
                          void* D, int64_t ldd, int M, int N, int K, const EpiParams& ep, cudaStream_t st);
 bool gemm_tcgen05_supported(int64_t lda, int64_t ldb, int64_t ldd, const void* A, const void* B, int M, int N, int K);
@@ -110,6 +112,16 @@ extern "C" int reed_gemm(int act_dtype, const void* A, int64_t lda, int a_mn_maj
     return gemm_tcgen05(A, lda, a_mn_major, B, ldb, b_mn_major, D, ldd, d_dtype, M, N, K, ep, st);
   }
   return gemm_simt(act_dtype, A, lda, a_mn_major, B, ldb, b_mn_major, D, ldd, d_dtype, M, N, K, ep, st);
+}
+
+// Weight and bias gradient of a Linear whose contraction is the batch (rows <= 64: the adaLN modulation / embedder linears):
+// dW[n_out, k_in] (+)= dy^T x, db[n_out] += column sums of dy (db may be NULL).  dy [rows, n_out] fp32 or bf16, x [rows, k_in].
+extern "C" int reed_outer_wgrad(const void* dy, int dy_dtype, int64_t ld_dy, const void* x, int x_dtype, int64_t ld_x, void* dW,
+                                int64_t ldd, void* db, int n_out, int k_in, int rows, int accumulate, void* stream) {
+  REED_REQUIRE(dy != nullptr && x != nullptr && dW != nullptr, "outer_wgrad: null operand");
+  REED_REQUIRE(n_out > 0 && k_in > 0, "outer_wgrad: empty output");
+  return outer_wgrad(dy_dtype, dy, ld_dy, x_dtype, x, ld_x, (float*)dW, ldd, n_out, k_in, rows, accumulate, (float*)db,
+                     (cudaStream_t)stream);
 }
 
 // Several linears that share their input as ONE tensor-core launch (the adaLN-Zero modulation linears of all blocks,

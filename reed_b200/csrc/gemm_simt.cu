@@ -80,110 +80,147 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const TA* __restrict__ A
 }
 
 // ------------------------------------------------------------------------------------------------
-// Weight gradient over a handful of rows: D[N, K] (+)= sum_b dy[b, N] * x[b, K], b < 64 (the adaLN / embedder linears,
+// Weight gradient over a handful of rows: D[N, K] (+)= sum_b dy[b, N] * x[b, K], b <= 64 (the adaLN / embedder linears,
 // whose contraction is the batch).  An outer-product stream: 2 small operand tiles in shared memory, every thread
-// owns a 4 x 4 output block, rows written as coalesced float4 - bounded by the HBM write of N*K floats.
+// owns an 8 x 4 output block, rows written as coalesced float4 - bounded by the HBM write of N*K floats.
+// dy and x may differ in type (the adaLN modulation gradient stays fp32, silu(c) is bf16); with `db` the CTAs of the
+// first column tile also add the column sums of dy into it (the bias gradient, no separate pass over dy).
 // ------------------------------------------------------------------------------------------------
 constexpr int kOwN = 64, kOwK = 128;
 
-// CTA = 64 x 128 outputs, thread = 8 rows x 4 columns; the batch rows of dy / x are staged in shared memory as fp32.
-// Row pairs ride on the packed fp32 FMA (FFMA2): 16 issue slots per batch row for 32 FMAs, operands from three
-// LDS.128 (the dy values are a warp-wide broadcast).  The kernel is bound by its M*N fp32 writes.
-template <typename TA>
-__global__ void __launch_bounds__(256) outer_wgrad_kernel(const TA* __restrict__ dy, int64_t ld_dy, const TA* __restrict__ x,
-                                                           int64_t ld_x, float* __restrict__ D, int64_t ldd, int N, int K,
-                                                           int B, int accumulate) {
-  pdl_launch();   // dependents (the next GEMM of the stream) may start their prologue
-  __shared__ __align__(16) float sdy[64][kOwN];
-  __shared__ __align__(16) float sx[64][kOwK];
-  const int tid = threadIdx.x;
-  const int n0 = blockIdx.y * kOwN, k0 = blockIdx.x * kOwK;
-  constexpr bool kBf = sizeof(TA) == 2;
-  const bool fast = kBf && n0 + kOwN <= N && k0 + kOwK <= K && ld_dy % 8 == 0 && ld_x % 8 == 0 &&
-                    (((uintptr_t)dy | (uintptr_t)x) & 15) == 0;
+// rows [0, B) x `width` columns starting at column c0 of a row-major matrix -> fp32 shared memory [B][width]
+template <typename T, int WIDTH>
+__device__ __forceinline__ void ow_stage(const T* __restrict__ src, int64_t ld, int c0, int cols, int B, float* dst, int tid) {
+  constexpr int kVec = sizeof(T) == 2 ? 8 : 4;     // elements per 16-byte load
+  const bool fast = c0 + WIDTH <= cols && ld % kVec == 0 && ((uintptr_t)src & 15) == 0;
   if (fast) {
-    // 8 bf16 per 16-byte load
-    for (int e = tid; e < B * (kOwN / 8); e += 256) {
-      const int b = e / (kOwN / 8), c = e % (kOwN / 8);
-      const uint4 v = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(dy) + (int64_t)b * ld_dy + n0 + c * 8));
-      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        sdy[b][c * 8 + 2 * i] = __low2float(h[i]);
-        sdy[b][c * 8 + 2 * i + 1] = __high2float(h[i]);
-      }
-    }
-    for (int e = tid; e < B * (kOwK / 8); e += 256) {
-      const int b = e / (kOwK / 8), c = e % (kOwK / 8);
-      const uint4 v = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(x) + (int64_t)b * ld_x + k0 + c * 8));
-      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        sx[b][c * 8 + 2 * i] = __low2float(h[i]);
-        sx[b][c * 8 + 2 * i + 1] = __high2float(h[i]);
+    for (int e = tid; e < B * (WIDTH / kVec); e += 256) {
+      const int b = e / (WIDTH / kVec), c = e % (WIDTH / kVec);
+      const uint4 v = __ldg(reinterpret_cast<const uint4*>(src + (int64_t)b * ld + c0 + c * kVec));
+      float* o = dst + b * WIDTH + c * kVec;
+      if constexpr (sizeof(T) == 2) {
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+        *reinterpret_cast<float4*>(o) = make_float4(__low2float(h[0]), __high2float(h[0]), __low2float(h[1]), __high2float(h[1]));
+        *reinterpret_cast<float4*>(o + 4) = make_float4(__low2float(h[2]), __high2float(h[2]), __low2float(h[3]), __high2float(h[3]));
+      } else {
+        *reinterpret_cast<uint4*>(o) = v;
       }
     }
   } else {
-    for (int e = tid; e < B * kOwN; e += 256) {
-      const int b = e / kOwN, n = e % kOwN;
-      sdy[b][n] = (n0 + n < N) ? to_f(dy[(int64_t)b * ld_dy + n0 + n]) : 0.f;
+    for (int e = tid; e < B * WIDTH; e += 256) {
+      const int b = e / WIDTH, c = e % WIDTH;
+      dst[b * WIDTH + c] = (c0 + c < cols) ? to_f(src[(int64_t)b * ld + c0 + c]) : 0.f;
     }
-    for (int e = tid; e < B * kOwK; e += 256) {
-      const int b = e / kOwK, k = e % kOwK;
-      sx[b][k] = (k0 + k < K) ? to_f(x[(int64_t)b * ld_x + k0 + k]) : 0.f;
-    }
-  }
-  __syncthreads();
-  const int tk = (tid & 31) * 4, tn = (tid >> 5) * 8;
-  float2 acc[4][4];   // [row pair][column]: (row 2p, row 2p+1)
-#pragma unroll
-  for (int p = 0; p < 4; ++p)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) acc[p][j] = make_float2(0.f, 0.f);
-#pragma unroll 4
-  for (int b = 0; b < B; ++b) {
-    const float4 a0 = *reinterpret_cast<const float4*>(&sdy[b][tn]);     // same address across the warp: broadcast
-    const float4 a1 = *reinterpret_cast<const float4*>(&sdy[b][tn + 4]);
-    const float4 x4 = *reinterpret_cast<const float4*>(&sx[b][tk]);
-    const float2 ap[4] = {make_float2(a0.x, a0.y), make_float2(a0.z, a0.w), make_float2(a1.x, a1.y), make_float2(a1.z, a1.w)};
-    const float xv[4] = {x4.x, x4.y, x4.z, x4.w};
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float2 xx = make_float2(xv[j], xv[j]);
-#pragma unroll
-      for (int p = 0; p < 4; ++p) acc[p][j] = __ffma2_rn(ap[p], xx, acc[p][j]);
-    }
-  }
-  const int col = k0 + tk;
-  if (col >= K) return;
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int row = n0 + tn + i;
-    if (row >= N) continue;
-    float* d = D + (int64_t)row * ldd + col;
-    const int p = i >> 1;
-    F4 o;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) o.v[j] = (i & 1) ? acc[p][j].y : acc[p][j].x;
-    if (accumulate) {
-      const F4 old = load4(d);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) o.v[j] += old.v[j];
-    }
-    store4(d, o);
   }
 }
 
-// D[M_out = N of dy, N_out = K of x]: called through gemm_simt's interface (a_mn && b_mn, contraction <= 64)
-static int outer_wgrad(int act_dtype, const void* A, int64_t lda, const void* B, int64_t ldb, float* D, int64_t ldd, int M,
-                       int N, int K, int accumulate, cudaStream_t st) {
-  dim3 grid(ceil_div(N, kOwK), ceil_div(M, kOwN));
-  if (act_dtype == kBF16)
-    outer_wgrad_kernel<bf16><<<grid, 256, 0, st>>>((const bf16*)A, lda, (const bf16*)B, ldb, D, ldd, M, N, K, accumulate);
-  else
-    outer_wgrad_kernel<float><<<grid, 256, 0, st>>>((const float*)A, lda, (const float*)B, ldb, D, ldd, M, N, K, accumulate);
-  REED_LAUNCH_CHECK();
+// CTA = 64 x 128 outputs, thread = 8 rows x 4 columns; the batch rows of dy / x are staged in shared memory as fp32
+// (dynamic, B * 192 floats).  Three CTAs fit an SM (70 registers): a CTA takes as many consecutive column tiles of its
+// row strip as it needs for the grid to be one wave (3 of 9 at the adaLN shape: 324 CTAs instead of 972 in 2.2 waves).
+// Row pairs ride on the packed fp32 FMA (FFMA2): 16 issue slots per batch row for 32 FMAs, operands from three
+// LDS.128 (the dy values are a warp-wide broadcast).  The kernel is bound by its M*N fp32 writes.
+template <typename TDY, typename TX>
+__global__ void __launch_bounds__(256) outer_wgrad_kernel(const TDY* __restrict__ dy, int64_t ld_dy, const TX* __restrict__ x,
+                                                           int64_t ld_x, float* __restrict__ D, int64_t ldd, int N, int K,
+                                                           int B, int accumulate, float* __restrict__ db, int kt_per_cta) {
+  pdl_launch();   // dependents (the next GEMM of the stream) may start their prologue
+  extern __shared__ __align__(16) float ow_smem[];
+  float* sdy = ow_smem;                    // [B][kOwN]
+  float* sx = ow_smem + B * kOwN;          // [B][kOwK]
+  const int tid = threadIdx.x;
+  const int n0 = blockIdx.y * kOwN;
+  const int tiles_k = (K + kOwK - 1) / kOwK;
+  const int kt0 = blockIdx.x * kt_per_cta, kt1 = min(kt0 + kt_per_cta, tiles_k);
+  pdl_wait();
+  ow_stage<TDY, kOwN>(dy, ld_dy, n0, N, B, sdy, tid);
+  const int tk = (tid & 31) * 4, tn = (tid >> 5) * 8;
+  for (int kt = kt0; kt < kt1; ++kt) {       // the CTA's column tiles share the staged dy tile
+    const int k0 = kt * kOwK;
+    if (kt > kt0) __syncthreads();           // everyone is done reading the previous x tile
+    ow_stage<TX, kOwK>(x, ld_x, k0, K, B, sx, tid);
+    __syncthreads();
+    if (db != nullptr && kt == 0 && tid < kOwN && n0 + tid < N) {     // bias gradient: column sums of dy
+      float sum = 0.f;
+      for (int b = 0; b < B; ++b) sum += sdy[b * kOwN + tid];
+      db[n0 + tid] += sum;
+    }
+    float2 acc[4][4];   // [row pair][column]: (row 2p, row 2p+1)
+#pragma unroll
+    for (int p = 0; p < 4; ++p)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[p][j] = make_float2(0.f, 0.f);
+#pragma unroll 4
+    for (int b = 0; b < B; ++b) {
+      const float4 a0 = *reinterpret_cast<const float4*>(&sdy[b * kOwN + tn]);     // same address across the warp: broadcast
+      const float4 a1 = *reinterpret_cast<const float4*>(&sdy[b * kOwN + tn + 4]);
+      const float4 x4 = *reinterpret_cast<const float4*>(&sx[b * kOwK + tk]);
+      const float2 ap[4] = {make_float2(a0.x, a0.y), make_float2(a0.z, a0.w), make_float2(a1.x, a1.y), make_float2(a1.z, a1.w)};
+      const float xv[4] = {x4.x, x4.y, x4.z, x4.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 xx = make_float2(xv[j], xv[j]);
+#pragma unroll
+        for (int p = 0; p < 4; ++p) acc[p][j] = __ffma2_rn(ap[p], xx, acc[p][j]);
+      }
+    }
+    const int col = k0 + tk;
+    if (col >= K) continue;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int row = n0 + tn + i;
+      if (row >= N) continue;
+      float* d = D + (int64_t)row * ldd + col;
+      const int p = i >> 1;
+      F4 o;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) o.v[j] = (i & 1) ? acc[p][j].y : acc[p][j].x;
+      if (accumulate) {
+        const F4 old = load4(d);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) o.v[j] += old.v[j];
+      }
+      store4(d, o);
+    }
+  }
+}
+
+// D[N = columns of dy, K = columns of x] (+)= dy^T x, db[N] += column sums of dy (optional); B <= 64 rows
+template <typename TDY, typename TX>
+static int outer_wgrad_launch(const void* dy, int64_t ld_dy, const void* x, int64_t ld_x, float* D, int64_t ldd, int N, int K,
+                              int B, int accumulate, float* db, cudaStream_t st) {
+  auto kernel = outer_wgrad_kernel<TDY, TX>;
+  const int smem = B * (kOwN + kOwK) * 4;
+  static bool configured = false;
+  if (!configured) {
+    REED_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * (kOwN + kOwK) * 4));
+    configured = true;
+  }
+  const int tiles_k = ceil_div(K, kOwK), tiles_n = ceil_div(N, kOwN);
+  int kt_per_cta = ceil_div((int64_t)tiles_k * tiles_n, 3 * kNumSMs);
+  if (kt_per_cta > tiles_k) kt_per_cta = tiles_k;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(ceil_div(tiles_k, kt_per_cta), tiles_n);
+  cfg.blockDim = dim3(256);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  REED_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kernel, (const TDY*)dy, ld_dy, (const TX*)x, ld_x, D, ldd, N, K, B, accumulate, db,
+                                     kt_per_cta));
   return 0;
+}
+
+int outer_wgrad(int dy_dtype, const void* dy, int64_t ld_dy, int x_dtype, const void* x, int64_t ld_x, float* D, int64_t ldd,
+                int N, int K, int B, int accumulate, float* db, cudaStream_t st) {
+  REED_REQUIRE(B >= 1 && B <= 64, "outer_wgrad: %d rows (1..64)", B);
+  REED_REQUIRE(K % 4 == 0 && ldd % 4 == 0 && ((uintptr_t)D & 15) == 0, "outer_wgrad: the output needs 16-byte rows");
+  if (dy_dtype == kBF16 && x_dtype == kBF16) return outer_wgrad_launch<bf16, bf16>(dy, ld_dy, x, ld_x, D, ldd, N, K, B, accumulate, db, st);
+  if (dy_dtype == kF32 && x_dtype == kBF16) return outer_wgrad_launch<float, bf16>(dy, ld_dy, x, ld_x, D, ldd, N, K, B, accumulate, db, st);
+  if (dy_dtype == kF32 && x_dtype == kF32) return outer_wgrad_launch<float, float>(dy, ld_dy, x, ld_x, D, ldd, N, K, B, accumulate, db, st);
+  return fail("outer_wgrad: unsupported operand types (dy %d, x %d)", dy_dtype, x_dtype);
 }
 
 int gemm_simt(int act_dtype, const void* A, int64_t lda, int a_mn, const void* B, int64_t ldb, int b_mn, void* D,
@@ -191,7 +228,7 @@ int gemm_simt(int act_dtype, const void* A, int64_t lda, int a_mn, const void* B
   REED_REQUIRE(N % 4 == 0 && ldd % 4 == 0, "gemm_simt needs N %% 4 == 0 and ldd %% 4 == 0 (N=%d ldd=%lld)", N, (long long)ldd);
   // batch-contraction weight gradient (A = dy stored [K, M], B = x stored [K, N], K <= 64 rows): outer-product stream
   if (a_mn && b_mn && K <= 64 && d_dtype == kF32 && ep.kind == kEpiNone && ep.bias == nullptr && (int64_t)M * N >= 65536)
-    return outer_wgrad(act_dtype, A, lda, B, ldb, (float*)D, ldd, M, N, K, ep.accumulate, st);
+    return outer_wgrad(act_dtype, A, lda, act_dtype, B, ldb, (float*)D, ldd, M, N, K, ep.accumulate, nullptr, st);
   dim3 grid(ceil_div(N, SBN), ceil_div(M, SBM));
   int k_per_split = K > 0 ? K : 1;
   // few output tiles and a long reduction (patch-embed / final-layer wgrad): split K across the machine

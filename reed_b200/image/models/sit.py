@@ -275,7 +275,10 @@ class SiT(nn.Module):
         z_img = z_txt = None
         # adaLN_modulation(c) of all blocks in one grouped GEMM (the weights stay separate parameters)
         ada_lin = [blk.adaLN_modulation[1] for blk in self.blocks]
-        ada_all = ops.AdaLNAll(c_act, ada_lin, act_dtype, c_acc) if ops.AdaLNAll.usable(c_act, ada_lin, act_dtype) else None
+        # (a trainer whose blocks receive their operands by per-block all-gathers under the forward turns this off: the
+        # grouped GEMM would read every block's weights at the start of the step)
+        grouped = getattr(self, "_reed_adaln_grouped", True) and ops.AdaLNAll.usable(c_act, ada_lin, act_dtype)
+        ada_all = ops.AdaLNAll(c_act, ada_lin, act_dtype, c_acc) if grouped else None
         for i, blk in enumerate(self.blocks, start=1):
             tok = blk(tok, c_act, act_dtype, c_acc, (ada_all, i - 1) if ada_all is not None else None)
             if inference:

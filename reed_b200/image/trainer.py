@@ -301,6 +301,9 @@ class ReedTrainer:
         self._state_complete = True          # ... and of the masters / EMA / moments (gather_state() completes them)
         self._step_dev = torch.zeros(1, device=dev, dtype=torch.int32)   # device copy of step_count (graph replays)
         self._graph = None
+        # NCCL form of the sharded step: block i's operands arrive by an all-gather awaited in block i's forward pre-hook,
+        # so nothing may read all blocks' weights up front (the multicast form opens the step with one barrier instead)
+        model._reed_adaln_grouped = not (self.shard and self.nvls is None)
         # all-reduce each block's bucket as soon as that block's backward has produced its last gradient
         for i, blk in enumerate(model.blocks):
             bucket = self.state.bucket_of_block(i)

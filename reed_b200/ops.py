@@ -394,6 +394,32 @@ def _bias_grad(p, dy2d):
     return out
 
 
+def outer_wgrad(dy, x, dw, db, accumulate):
+    """dw[N,K] (+)= dy^T x and db[N] += colsum(dy) for a handful of rows (the batch is the contraction): reed_outer_wgrad.
+    dy [B,N] fp32 or bf16, x [B,K]; db may be None."""
+    B, N = dy.shape
+    K = x.shape[1]
+    assert x.shape[0] == B and dw.shape == (N, K) and dw.dtype == torch.float32 and dw.stride(1) == 1
+    assert dy.stride(1) == 1 and x.stride(1) == 1 and (db is None or (db.dtype == torch.float32 and db.is_contiguous()))
+    _launch("reed_outer_wgrad", _p(dy), _code(dy.dtype), dy.stride(0), _p(x), _code(x.dtype), x.stride(0), _p(dw), dw.stride(0),
+            _p(db), N, K, B, int(accumulate), _stream())
+
+
+def _outer_weight_and_bias_grad(w, b, dy, x):
+    """Gradients of a Linear applied to a [B <= 64, K] input, both from one outer-product pass over the fp32 dy."""
+    wmain, wacc = _grad_target(w)
+    dw = wmain.view(w.shape) if wmain is not None else torch.empty(w.shape, device=dy.device, dtype=torch.float32)
+    bmain, bacc = _grad_target(b)
+    if bmain is not None:
+        if not bacc:
+            _zero_fresh(b, bmain)
+        dbuf = bmain
+    else:
+        dbuf = torch.zeros(b.shape, device=dy.device, dtype=torch.float32)
+    outer_wgrad(dy, x, dw, dbuf, wacc)
+    return (None if wmain is not None else dw), (None if bmain is not None else dbuf)
+
+
 class LinearFn(torch.autograd.Function):
     """y = act(x W^T + b).  x: [M,K] fp32 or act dtype; W: fp32 master [N,K]; output dtype selectable."""
 
@@ -469,7 +495,8 @@ class AdaLNAll:
         bias_all = torch.cat([l.bias.detach() for l in linears])
         self.mod_all = torch.empty((c_act.shape[0], self.width * len(linears)), device=c_act.device, dtype=torch.float32)
         gemm_grouped_fwd(c_act, self.weights, bias_all, self.mod_all)
-        self.dmods = [None] * len(linears)
+        self.dmod_all = None                 # fp32 [L, B, 6D], zeroed by the first block that runs backward
+        self.done = []                       # blocks whose dmod is complete
         self.c_acc = c_acc
         if c_acc is not None:
             c_acc.deferred.append(self._input_grad)
@@ -485,12 +512,20 @@ class AdaLNAll:
     def mod(self, i):
         return self.mod_all[:, i * self.width:(i + 1) * self.width]
 
+    def dmod(self, i):
+        """Block i's gradient buffer for its modulation vectors (the row-wise backward kernels add into it)."""
+        if self.dmod_all is None:
+            self.dmod_all = torch.zeros((len(self.weights), self.c_act.shape[0], self.width), device=self.c_act.device,
+                                        dtype=torch.float32)
+        return self.dmod_all[i]
+
     def _input_grad(self):
-        done = [i for i, d in enumerate(self.dmods) if d is not None]
-        if not done:
+        if not self.done:
             return
-        gemm_grouped_dgrad([self.dmods[i] for i in done], [self.weights[i] for i in done], self.c_acc.get(self.c_act), True)
-        self.dmods = [None] * len(self.dmods)
+        dmod_a = cast(self.dmod_all, self.c_act.dtype)          # one cast for all blocks
+        done = sorted(self.done)
+        gemm_grouped_dgrad([dmod_a[i] for i in done], [self.weights[i] for i in done], self.c_acc.get(self.c_act), True)
+        self.done, self.dmod_all = [], None
 
 
 class SiluCastFn(torch.autograd.Function):
@@ -643,7 +678,7 @@ class SiTBlockFn(torch.autograd.Function):
         if dx2.dtype != torch.float32:
             dx2 = cast(dx2, torch.float32)
         sh_a, sc_a, g_a, sh_m, sc_m, g_m = (mod[:, i * D:(i + 1) * D] for i in range(6))
-        dmod = torch.zeros_like(mod)
+        dmod = ctx.ada[0].dmod(ctx.ada[1]) if ctx.ada is not None else torch.zeros_like(mod)
         dsh_a, dsc_a, dg_a, dsh_m, dsc_m, dg_m = (dmod[:, i * D:(i + 1) * D] for i in range(6))
 
         def bias_buffer(p):
@@ -689,13 +724,22 @@ class SiTBlockFn(torch.autograd.Function):
         dx0 = ln_modulate_bwd(dxm1, x0, mean1, rstd1, sc_a, T, dx1, dsh_a, dsc_a)
 
         # ---- adaLN linear:  mod = c_act W_ada^T + b_ada
+        dc = None
+        if ctx.ada is not None:
+            # weight and bias gradient in one outer-product pass over the fp32 dmod; the block's share of dL/d silu(c) is
+            # part of one grouped GEMM over all blocks, run when that gradient is collected (AdaLNAll._input_grad)
+            dw_ada, db_ada = off_stream(lambda: _outer_weight_and_bias_grad(w_ada, b_ada, dmod, c_act), dmod, c_act)
+            ctx.ada[0].done.append(ctx.ada[1])
+            if side is not None:
+                side.join()
+            if ctx.after_backward is not None:
+                ctx.after_backward()
+            return (dx0.view(B, T, D), dc, dw_ada, db_ada, dwqkv, dbqkv, dwp, dbp, dw1, db1, dw2, db2, None, None, None,
+                    None) + qk_grads + (None,)
         dmod_a = cast(dmod, act_dtype)
         db_ada = _bias_grad(b_ada, dmod)
         dw_ada = off_stream(lambda: _weight_grad(w_ada, dmod_a, c_act), dmod_a, c_act)
-        dc = None
-        if ctx.ada is not None and ctx.ada[0].c_acc is not None:
-            ctx.ada[0].dmods[ctx.ada[1]] = dmod_a      # its share of dL/d silu(c): one grouped GEMM for all blocks, later
-        elif ctx.needs_input_grad[1]:
+        if ctx.needs_input_grad[1]:
             if ctx.c_acc is not None:     # [B, 6D] x [6D, D]: few rows, long reduction -> split-K slices add into the side buffer
                 gemm(dmod_a, W(w_ada), b_mn=True, out=ctx.c_acc.get(c_act), accumulate=True)
             else:

@@ -176,6 +176,26 @@ def test_gemm_grouped_adaln(ops, shape):
     assert _rel(dc, want2) < 2e-3
 
 
+@pytest.mark.parametrize("shape", [(32, 6912, 1152), (4, 768, 128), (64, 200, 72), (7, 1536, 260)])   # (batch, n_out, k_in)
+@pytest.mark.parametrize("dy_dtype", [torch.float32, torch.bfloat16])
+def test_outer_wgrad_with_bias(ops, shape, dy_dtype):
+    """reed_outer_wgrad: dW (+)= dy^T x and db += colsum(dy) for a batch-sized contraction (autograd of adaLN_modulation,
+    sit.py:125-128), fp32 or bf16 dy against a bf16 input."""
+    B, N, K = shape
+    dy = _rand(B, N, dtype=dy_dtype, seed=1)
+    x = _rand(B, K, dtype=torch.bfloat16, seed=2)
+    dw = torch.full((N, K), 3.0, device=DEV)
+    db = torch.full((N,), 0.5, device=DEV)
+    ops.outer_wgrad(dy, x, dw, db, accumulate=False)
+    want_w = dy.float().t() @ x.float()
+    want_b = 0.5 + dy.float().sum(0)
+    assert _rel(dw, want_w) < 1e-5
+    assert _rel(db, want_b) < 1e-5
+    ops.outer_wgrad(dy, x, dw, None, accumulate=True)
+    assert _rel(dw, 2 * want_w) < 1e-5
+    assert _rel(db, want_b) < 1e-5
+
+
 @pytest.mark.parametrize("bn", [0, 1, 2, 3])                   # planner's choice / tile width 128 / 192 / 256
 @pytest.mark.parametrize("cg", [1, 2])
 def test_gemm_gate_residual_many_tiles(ops, bn, cg):

@@ -299,7 +299,10 @@ def test_trainer_graph_replay_matches_eager(precision):
 
     l_e, p_e, ema_e = run(False)
     l_g, p_g, ema_g = run(True)
-    tol = 1e-6 if precision == "fp32" else 1e-5     # same kernels on the same data: only atomics ordering differs
+    # same kernels on the same data: only atomics ordering differs.  bf16: the grouped adaLN input gradient adds a dozen
+    # split-K slices into a [B, D] buffer with fp32 atomics; eager runs differ from each other by up to 2.5e-5 after Adam
+    # has normalised a last-bit difference (profiles/noise_check.py, also under CUDA_LAUNCH_BLOCKING=1)
+    tol = 1e-6 if precision == "fp32" else 5e-5
     for a, b in zip(l_e, l_g):
         assert abs(a - b) <= tol * max(1.0, abs(a)), (l_e, l_g)
     # Adam normalises the update: where a gradient is ~0 an atomics-ordering difference in its last bits can move a
