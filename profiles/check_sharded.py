@@ -68,10 +68,13 @@ def main():
                     named[f"{name}/{field}"] = getattr(b, field)[off:off + p.numel()].float().clone()
         results.append((losses, named, float(tr.grad_norm())))
     (l0, n0, g0), (l1, n1, g1) = results
-    # fp32 buffers: absolute 5e-4 (Adam turns last-bit gradient noise - atomics ordering differs between a graph replay and
-    # eager launches - into steps of up to lr = 1e-4); bf16 shadows: one bf16 ulp of the value on top of that
+    # fp32 buffers: Adam's normalised step is at most lr = 1e-4 per step, and where the true gradient is zero (the key third
+    # of attn.qkv.bias - softmax is invariant to it) the sign of the computed gradient is rounding noise: two arithmetic
+    # paths (atomics ordering; the NCCL-sharded trainer runs the adaLN linears per block, the replicated one grouped) can
+    # drift apart by lr per step.  Bound: 1.1 lr per step taken; bf16 shadows: one bf16 ulp of the value on top of that
+    drift = 1.1e-4 * (args.steps + 2)
     def excess(k):
-        tol = 5e-4 + (n0[k].abs() * 2.0 ** -7 if k.endswith("/shadow") else 0.0)
+        tol = drift + (n0[k].abs() * 2.0 ** -7 if k.endswith("/shadow") else 0.0)
         return float(((n0[k] - n1[k]).abs() - tol).max())
     worst = max((excess(k), k) for k in n0)
     ok = all(abs(a - b) <= 1e-4 * max(1.0, abs(a)) for a, b in zip(l0, l1)) and worst[0] <= 0.0 \
@@ -82,8 +85,9 @@ def main():
         print(f"losses replicated {l0}\nlosses sharded    {l1}\ngrad norm {g0} vs {g1}\nworst excess over tolerance {worst}")
         print("SHARDED OPTIMIZER", "OK" if int(flag) else "MISMATCH")
     dist.barrier()
-    dist.destroy_process_group()
-    sys.exit(0 if int(flag) else 1)
+    torch.cuda.synchronize()
+    sys.stdout.flush()
+    os._exit(0 if int(flag) else 1)     # (destroy_process_group after graph captures on the NCCL streams can hang)
 
 
 if __name__ == "__main__":
