@@ -205,8 +205,8 @@ int gemm_tcgen05(const void* A, int64_t lda, int a_mn, const void* B, int64_t ld
   // REED_TMA_EPI: bit 0 = activation-gradient kinds (fused operand), bit 1 = activation kinds, bit 2 = plain bf16 stores
   // bit 3 = gate+residual (fp32 D updated in place in a ring of residual boxes, epilogue_loop_tma_gateres) - for short
   // reductions only (attn.proj): the ring takes shared memory from the operand pipeline, and a long main loop (mlp.fc2)
-  // loses more to a shallower pipeline than its last tile's epilogue gains (REED_GATERES_MAX_K: profiling knob)
-  static const int gateres_max_k = getenv("REED_GATERES_MAX_K") ? atoi(getenv("REED_GATERES_MAX_K")) : 2048;
+  // loses more to a shallower pipeline than its last tile's epilogue gains (measured equal at K = 4608)
+  constexpr int gateres_max_k = 2048;
   const int kind_bit = ep.kind == kEpiGateRes ? 8 : ((ep.kind == kEpiDGelu || ep.kind == kEpiDSilu) ? 1 : ((ep.kind == kEpiGelu || ep.kind == kEpiSilu) ? 2 : 4));
   const bool gate_res = ep.kind == kEpiGateRes && d_dtype == kF32 && ep.rows_per_group % 32 == 0 && K <= gateres_max_k;
   bool tma = (tma_epi_on & kind_bit) && !p.stream_k && !ep.accumulate && ((d_dtype == kBF16 && act_kind) || gate_res) &&

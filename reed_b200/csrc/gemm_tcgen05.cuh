@@ -509,10 +509,10 @@ __device__ __forceinline__ void epilogue_loop_tma(const EpiParams& ep, const Epi
 // (<= 128 bytes) per 4 cycles, whatever the row length: 16-column boxes (64-byte rows, the first version) capped the
 // epilogue at 3 TB/s chip-wide, so chunks are 32 columns - 128-byte fp32 rows (SWIZZLE_128B), 64-byte bf16 rows.
 // (2) Residual bytes in flight: every warp owns a ring of R residual boxes ([32 x 32] fp32, 4 KB), the requests for the
-// next R - 1 chunks outstanding while one is worked on, across tile boundaries; R is a launch parameter (host: as many as leave three operand stages).  A box is
-// updated IN PLACE (thread = row) and stored back by TMA; its slot is re-requested one chunk later, once the store has
-// read it.  y leaves through one [32 x 32] bf16 box (2 KB).  Shared memory is what this epilogue competes for with the
-// operand pipeline (fc2: 6 -> 3 stages cost 72 -> 89 us of main loop), hence the lean ring: R = 2, 10 KB per warp.
+// next R - 1 chunks outstanding while one is worked on, across tile boundaries (R is a launch parameter; the host passes 2).
+// A box is updated IN PLACE (thread = row) and stored back by TMA; its slot is re-requested one chunk later, once the
+// store has read it.  y leaves through one [32 x 32] bf16 box (2 KB).  Shared memory is what this epilogue competes for
+// with the operand pipeline (fc2: 6 -> 3 stages cost 72 -> 89 us of main loop), hence the lean ring: 10 KB per warp.
 // Bias and gate ride in one register each per chunk: lane l holds bias[col0 + l] / gate[g, col0 + l].
 constexpr int kGateResSlotBytes = 4096;
 constexpr int kGateResMaxSlots = 8;
@@ -930,12 +930,10 @@ static int launch(const CUtensorMap& ma, const CUtensorMap& mb, void* D, int64_t
   const bool fused_operand = ep.kind == kEpiDGelu || ep.kind == kEpiDSilu;
   int epi_bytes = tma_epi ? (fused_operand ? Cfg::kTmaEpiAuxBytes : Cfg::kTmaEpiBytes) : Cfg::kStagingBytes;
   if (tma_epi && sizeof(TD) == 4) {
-    // gate+residual: residual ring slots per epilogue warp (two by default: the ring competes with the operand stages for
-    // shared memory); tile configurations whose stages are too large for that keep the register epilogue
-    // (REED_GATERES_SLOTS: profiling knob)
-    static const int want = getenv("REED_GATERES_SLOTS") ? atoi(getenv("REED_GATERES_SLOTS")) : 2;
-    int R = want < 2 ? 2 : (want > kGateResMaxSlots ? kGateResMaxSlots : want);
-    while (R > 2 && Cfg::stages_for(kEpiWarps * gateres_warp_bytes(R)) < 3) --R;
+    // gate+residual: two residual ring slots per epilogue warp (the ring competes with the operand stages for shared
+    // memory; deeper rings measured no faster, profiles/r02_gemm_notes.md); tile configurations whose stages are too
+    // large even for that keep the register epilogue
+    constexpr int R = 2;
     if (Cfg::stages_for(kEpiWarps * gateres_warp_bytes(R)) >= 3) {
       tma_epi = R;
       epi_bytes = kEpiWarps * gateres_warp_bytes(R);
