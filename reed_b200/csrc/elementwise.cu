@@ -38,6 +38,12 @@ __device__ __forceinline__ void row_bar_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
   }
 }
+// one lane of a converged warp
+__device__ __forceinline__ bool row_elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 // bytes: multiple of 16; src, dst 16-byte aligned
 __device__ __forceinline__ void row_bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -218,7 +224,9 @@ __host__ __device__ inline int row_slot_bytes(int D, bool has_res) {
 // - two shuffle reductions, a CTA barrier, the cross-warp sum, address arithmetic - was 4/5 of the 256 instructions a
 // warp issued per row and the kernels ran at 0.56-0.67 issue utilisation, 0.65-0.73 of the HBM rate (ncu,
 // profiles/r02_ncu_row_bwd.txt); twelve elements per thread amortise it.
-template <typename TA, int V, bool LN, bool GATE>
+// FULL: D == 4 * V * team_threads, every thread owns V valid column groups - no per-group predicates (at D = 1152 they and
+// the divergence bookkeeping around them were a fifth of the 576 instructions a warp issued per row).
+template <typename TA, int V, bool LN, bool GATE, bool FULL>
 __global__ void __launch_bounds__(kRowMaxThreads, 1) row_bwd_kernel(const RowBwdParams p, int team_threads, int stages) {
   pdl_launch();   // dependents (the next GEMM of the stream) may start their prologue
   extern __shared__ __align__(128) uint8_t row_smem[];
@@ -272,7 +280,7 @@ __global__ void __launch_bounds__(kRowMaxThreads, 1) row_bwd_kernel(const RowBwd
 #pragma unroll
   for (int i = 0; i < V; ++i) {
     col[i] = (t + i * team_threads) * 4;
-    ok[i] = col[i] < D;
+    ok[i] = FULL || col[i] < D;
   }
   auto load_group = [&](int g) {              // per-group modulation vectors; column partial sums restart
 #pragma unroll
@@ -372,7 +380,12 @@ __global__ void __launch_bounds__(kRowMaxThreads, 1) row_bwd_kernel(const RowBwd
     // one team barrier per row: every thread of the team has copied its operands out of the slot (it can be refilled)
     // and, for LN, the per-warp partial sums are visible
     team_sync();
-    if (t == 0 && row + stages * teams < r1) issue(row + stages * teams, slot);
+    // the team's first warp refills the slot: a warp-uniform branch and an elected lane, so the bulk-copy operands sit in
+    // uniform registers (issued from a one-lane divergent branch each copy is wrapped in an R2UR waterfall loop)
+    if (t < 32 && row + stages * teams < r1) {
+      if (row_elect_one()) issue(row + stages * teams, slot);
+      __syncwarp();
+    }
     if (++slot == stages) { slot = 0; parity ^= 1u; }
     const int64_t base = (int64_t)row * D;
     if constexpr (LN) {
@@ -597,11 +610,12 @@ static int ln_fwd_dispatch(const float* x, const float* shift, const float* scal
 
 template <typename TA, bool LN, bool GATE>
 static int row_bwd_dispatch(RowBwdParams p, cudaStream_t st) {
-  auto kernel = row_bwd_kernel<TA, kRowV, LN, GATE>;
   const int D = p.D;
   const bool has_res = !LN || p.dres != nullptr;
   // a team = the threads of one row: kRowV float4 column groups each, whole warps (3 warps at D = 1152, 1 at D = 384)
   const int team_threads = ceil_div(ceil_div(D / 4, kRowV), 32) * 32;
+  const bool full = D == 4 * kRowV * team_threads;
+  auto kernel = full ? row_bwd_kernel<TA, kRowV, LN, GATE, true> : row_bwd_kernel<TA, kRowV, LN, GATE, false>;
   REED_REQUIRE(team_threads <= kRowMaxThreads, "row kernels: D = %d exceeds %d columns", D, kRowMaxThreads * kRowV * 4);
   int teams = kRowMaxThreads / team_threads;
   if (teams > kRowMaxTeams) teams = kRowMaxTeams;
@@ -613,10 +627,10 @@ static int row_bwd_dispatch(RowBwdParams p, cudaStream_t st) {
   while (stages < 2 && teams > 1) { --teams; stages = (200 * 1024) / (teams * slot); if (stages > kRowMaxStages) stages = kRowMaxStages; }
   REED_REQUIRE(stages >= 1, "row kernels: a row of D = %d does not fit the shared-memory ring", D);
   const int smem = teams * stages * slot;
-  static int configured = 0;     // per template instance
-  if (configured < smem) {
+  static int configured[2] = {0, 0};     // per template instance (FULL or not)
+  if (configured[full] < smem) {
     REED_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    configured = smem;
+    configured[full] = smem;
   }
   // one balanced wave: equal row ranges that may cross sample boundaries (a team flushes its column partials when the
   // group changes)
