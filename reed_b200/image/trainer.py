@@ -153,9 +153,14 @@ class FlatState:
     def begin_step(self):
         """Equivalent of optimizer.zero_grad(): kernel-written gradients are overwritten on their first write;
         gradients that arrive through autograd (the label-embedding table) are zeroed and accumulated into."""
+        # the 1-D gradient regions of all buckets (kernels add into them): one multi-tensor fill instead of one fill per
+        # bucket on first touch (29 launches per step on XL/2)
+        views = [b.zero_group.view for b in self.buckets if b.zero_group.view.numel() > 0]
+        if views and views[0].is_cuda:
+            torch._foreach_zero_(views)
         for b in self.buckets:
             b.work = None
-            b.zero_group.zeroed = False
+            b.zero_group.zeroed = bool(views) and views[0].is_cuda
             for p, off in zip(b.params, b.offsets):
                 if p._reed_kernel_grad:
                     p._reed_grad_fresh = True
