@@ -22,6 +22,7 @@ EPI_NONE, EPI_GELU, EPI_SILU, EPI_GATE_RES, EPI_DGELU, EPI_DSILU = range(6)
 ACT_NONE, ACT_GELU, ACT_SILU = 0, 1, 2
 BACKEND_AUTO, BACKEND_SIMT, BACKEND_TENSOR, BACKEND_TENSOR_CG1, BACKEND_TENSOR_CG2 = 0, 1, 2, 3, 4
 
+import ctypes as _ctypes
 import os as _os
 
 # profiling knob: 0 = bias gradients of qkv / fc1 by a separate column-sum pass instead of the ones-column GEMM
@@ -208,8 +209,8 @@ def wgrad_bias(dy2d, x_ext, k_in, dw, db, accumulate):
 
 
 def _ptr_table(tensors):
-    import ctypes
-    return (ctypes.c_void_p * len(tensors))(*[t.data_ptr() for t in tensors])
+    """Host array of device pointers (reed_gemm_grouped reads it during the call only)."""
+    return (_ctypes.c_void_p * len(tensors))(*[t.data_ptr() for t in tensors])
 
 
 def gemm_grouped_fwd(a, weights, bias_all, out):

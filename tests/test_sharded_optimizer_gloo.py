@@ -114,6 +114,9 @@ def _worker(rank, world, port, out):
         for tr in (rep, shd):
             _emulate_kernels(tr)
         ok = shd.shard and not rep.shard
+        # the NCCL form awaits each block's operands in that block's forward: nothing may read all blocks' weights at step
+        # start, so the grouped adaLN GEMM (ops.AdaLNAll) is off there and on for the replicated trainer
+        ok &= shd.model._reed_adaln_grouped is False and rep.model._reed_adaln_grouped is True
         # layout: block buckets hold 2-D weights only, in `world` equal 16-byte-aligned slices; 1-D parameters are replicated
         for b in shd.state.buckets:
             if b.name == "outer":
