@@ -139,7 +139,7 @@ class SiTBlock(nn.Module):
         self.mlp = _MlpParams(hidden_size, int(hidden_size * mlp_ratio))
         self.adaLN_modulation = nn.Sequential(nn.SiLU(), nn.Linear(hidden_size, 6 * hidden_size, bias=True))
 
-    def forward(self, x, c_act, act_dtype, c_acc=None, ada=None):
+    def forward(self, x, c_act, act_dtype, c_acc=None, ada=None, link_in=None, link_out=None):
         """x: (N,T,D) fp32; c_act = silu(c) already in the act dtype (shared by every block); c_acc: the side
         accumulator the block adds its gradient w.r.t. c_act into (ops.silu_cast); ada: (ops.AdaLNAll, block index) when
         the modulation vectors of all blocks were computed by one grouped GEMM."""
@@ -149,7 +149,7 @@ class SiTBlock(nn.Module):
                                     m.fc1.weight, m.fc1.bias, m.fc2.weight, m.fc2.bias, self.num_heads, act_dtype,
                                     getattr(self, "_reed_after_backward", None), c_acc,
                                     *((a.q_norm.weight, a.q_norm.bias, a.k_norm.weight, a.k_norm.bias) if self.qk_norm
-                                      else (None, None, None, None)), ada)
+                                      else (None, None, None, None)), ada, link_in, link_out)
 
 
 class FinalLayer(nn.Module):
@@ -279,8 +279,16 @@ class SiT(nn.Module):
         # grouped GEMM would read every block's weights at the start of the step)
         grouped = getattr(self, "_reed_adaln_grouped", True) and ops.AdaLNAll.usable(c_act, ada_lin, act_dtype)
         ada_all = ops.AdaLNAll(c_act, ada_lin, act_dtype, c_acc) if grouped else None
+        # consecutive blocks whose residual stream has no other consumer (no projector tap in between) share one fused
+        # kernel for the later block's LayerNorm backward and the earlier block's gate backward (ops.BlockLink)
+        taps = {self.encoder_depth, self.encoder_depth_text} if not inference else set()
+        link_in = None
+        depth = len(self.blocks)
         for i, blk in enumerate(self.blocks, start=1):
-            tok = blk(tok, c_act, act_dtype, c_acc, (ada_all, i - 1) if ada_all is not None else None)
+            link_out = (ops.BlockLink() if (ops._BLOCK_LINK and torch.is_grad_enabled() and tok.requires_grad and i < depth
+                                             and i not in taps) else None)
+            tok = blk(tok, c_act, act_dtype, c_acc, (ada_all, i - 1) if ada_all is not None else None, link_in, link_out)
+            link_in = link_out
             if inference:
                 continue
             if i == self.encoder_depth:

@@ -611,8 +611,27 @@ class LNModulateFn:
         return _lib().ln_modulate(x, shift, scale, act_dtype == torch.bfloat16)[0]
 
 
+class BlockLink:
+    """Hand-over between the backward passes of two consecutive blocks whose residual stream has no other consumer.
+
+    Block i+1's backward ends with the LayerNorm backward that produces dL/dx (= block i's incoming gradient); block i's
+    backward starts with the gate backward of its MLP branch on exactly that tensor.  The two are one pass of the fused
+    LN-backward -> gate-backward kernel (the same one a block uses internally for its attention branch): block i+1 runs it with
+    block i's saved branch output and gate, leaves dy / the bias-gradient handle / the modulation-gradient buffer here, and
+    block i picks them up instead of launching its own gate backward (one launch and one 38 MB re-read of the residual
+    gradient less per block).  REED_BLOCK_LINK=0 turns it off for A/B runs."""
+    __slots__ = ("y", "gate", "bias", "ada", "dy", "db_ret", "dmod", "dx_ptr")
+
+    def __init__(self):
+        self.y = self.gate = self.bias = self.ada = self.dy = self.db_ret = self.dmod = None
+        self.dx_ptr = 0
+
+
+_BLOCK_LINK = _os.environ.get("REED_BLOCK_LINK", "1") != "0"
+
+
 class SiTBlockFn(torch.autograd.Function):
-    """One adaLN-Zero transformer block (sit.py:125-137 + timm Attention/Mlp): 8 kernels forward, 20 backward.
+    """One adaLN-Zero transformer block (sit.py:125-137 + timm Attention/Mlp): 7 kernels forward, 16-17 backward.
 
     x: [B,T,D] fp32 residual stream; c_act: [B,D] = silu(c) in the act dtype (shared by all blocks).
     mod = c_act W_ada^T + b_ada = (shift_a, scale_a, gate_a, shift_m, scale_m, gate_m), fp32 [B,6D].
@@ -620,7 +639,8 @@ class SiTBlockFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, c_act, w_ada, b_ada, w_qkv, b_qkv, w_proj, b_proj, w_fc1, b_fc1, w_fc2, b_fc2, num_heads,
-                act_dtype, after_backward, c_acc=None, qn_w=None, qn_b=None, kn_w=None, kn_b=None, ada=None):
+                act_dtype, after_backward, c_acc=None, qn_w=None, qn_b=None, kn_w=None, kn_b=None, ada=None, link_in=None,
+                link_out=None):
         _require_cuda(x, c_act)
         B, T, D = x.shape
         M = B * T
@@ -661,6 +681,11 @@ class SiTBlockFn(torch.autograd.Function):
         ctx.after_backward = after_backward
         ctx.c_acc = c_acc
         ctx.ada = ada
+        # link_out: this block's output feeds the next block only, whose backward will run this block's MLP gate backward;
+        # link_in: the same for the previous block, seen from this one
+        if link_out is not None:
+            link_out.y, link_out.gate, link_out.bias, link_out.ada = y2, g_m, b_fc2, ada
+        ctx.link_in, ctx.link_out = link_in, link_out
         return x2.view(B, T, D)
 
     @staticmethod
@@ -679,7 +704,15 @@ class SiTBlockFn(torch.autograd.Function):
         if dx2.dtype != torch.float32:
             dx2 = cast(dx2, torch.float32)
         sh_a, sc_a, g_a, sh_m, sc_m, g_m = (mod[:, i * D:(i + 1) * D] for i in range(6))
-        dmod = ctx.ada[0].dmod(ctx.ada[1]) if ctx.ada is not None else torch.zeros_like(mod)
+        handed = ctx.link_out if (ctx.link_out is not None and ctx.link_out.dy is not None) else None
+        if handed is not None:
+            # the next block's backward already ran this block's MLP gate backward on the gradient it produced
+            if dx2.data_ptr() != handed.dx_ptr:
+                raise RuntimeError("reed_b200: a linked block received a gradient other than the one its successor produced "
+                                   "(its output has another consumer); build the model without BlockLink for this block")
+            dmod = handed.dmod
+        else:
+            dmod = ctx.ada[0].dmod(ctx.ada[1]) if ctx.ada is not None else torch.zeros_like(mod)
         dsh_a, dsc_a, dg_a, dsh_m, dsc_m, dg_m = (dmod[:, i * D:(i + 1) * D] for i in range(6))
 
         def bias_buffer(p):
@@ -692,8 +725,12 @@ class SiTBlockFn(torch.autograd.Function):
             return buf, buf
 
         # ---- MLP branch:  x2 = x1 + g_m * (gelu(xm2 W1^T + b1) W2^T + b2)
-        db2_buf, db2 = bias_buffer(b_fc2)
-        dy2 = gate_bwd(dx2, y2, g_m, T, dg_m, db2_buf)
+        if handed is not None:
+            dy2, db2 = handed.dy, handed.db_ret
+            handed.dy = handed.db_ret = handed.dmod = None
+        else:
+            db2_buf, db2 = bias_buffer(b_fc2)
+            dy2 = gate_bwd(dx2, y2, g_m, T, dg_m, db2_buf)
         side = _SideStream(dx2.device) if (_WGRAD_STREAM and _flat_grads(w_fc2, w_fc1, b_fc1, w_proj, w_qkv, b_qkv, w_ada)) else None
 
         def off_stream(fn, *operands):
@@ -722,7 +759,16 @@ class SiTBlockFn(torch.autograd.Function):
             qk_grads = tuple(rets)
         dwqkv, dbqkv = off_stream(lambda: _weight_and_bias_grad(w_qkv, b_qkv, dqkv, xm1, xm1_ext), dqkv, xm1s)
         dxm1 = gemm(dqkv, W(w_qkv), b_mn=True, out_dtype=act_dtype)
-        dx0 = ln_modulate_bwd(dxm1, x0, mean1, rstd1, sc_a, T, dx1, dsh_a, dsc_a)
+        L = ctx.link_in
+        if L is not None and L.y is not None:
+            # ... and the previous block's MLP gate backward rides on this block's first LayerNorm backward
+            dmod_prev = L.ada[0].dmod(L.ada[1]) if L.ada is not None else torch.zeros_like(mod)
+            dbq_buf, dbq_ret = bias_buffer(L.bias)
+            dx0, dy_prev = ln_modulate_gate_bwd(dxm1, x0, mean1, rstd1, sc_a, T, dx1, dsh_a, dsc_a, L.y, L.gate,
+                                                dmod_prev[:, 5 * D:6 * D], dbq_buf)
+            L.dy, L.db_ret, L.dmod, L.dx_ptr = dy_prev, dbq_ret, dmod_prev, dx0.data_ptr()
+        else:
+            dx0 = ln_modulate_bwd(dxm1, x0, mean1, rstd1, sc_a, T, dx1, dsh_a, dsc_a)
 
         # ---- adaLN linear:  mod = c_act W_ada^T + b_ada
         dc = None
@@ -736,7 +782,7 @@ class SiTBlockFn(torch.autograd.Function):
             if ctx.after_backward is not None:
                 ctx.after_backward()
             return (dx0.view(B, T, D), dc, dw_ada, db_ada, dwqkv, dbqkv, dwp, dbp, dw1, db1, dw2, db2, None, None, None,
-                    None) + qk_grads + (None,)
+                    None) + qk_grads + (None, None, None)
         dmod_a = cast(dmod, act_dtype)
         db_ada = _bias_grad(b_ada, dmod)
         dw_ada = off_stream(lambda: _weight_grad(w_ada, dmod_a, c_act), dmod_a, c_act)
@@ -750,7 +796,7 @@ class SiTBlockFn(torch.autograd.Function):
             side.join()                       # the bucket's gradients are complete on the current stream from here on
         if ctx.after_backward is not None:
             ctx.after_backward()
-        return (dx0.view(B, T, D), dc, dw_ada, db_ada, dwqkv, dbqkv, dwp, dbp, dw1, db1, dw2, db2, None, None, None, None) + qk_grads + (None,)
+        return (dx0.view(B, T, D), dc, dw_ada, db_ada, dwqkv, dbqkv, dwp, dbp, dw1, db1, dw2, db2, None, None, None, None) + qk_grads + (None, None, None)
 
 
 # --------------------------------------------------------------------------------------------------

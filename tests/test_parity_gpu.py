@@ -383,3 +383,35 @@ def test_grouped_adaln_matches_per_block_gemms():
         assert float(cos) > 0.9999, (name, float(cos))
     for name in ("t_embedder.mlp.0.weight", "y_embedder.embedding_table.weight"):
         assert _rel(g_g[name], g_b[name]) < 1e-2, name
+
+
+@pytest.mark.parametrize("precision", ["bf16", "fp32"])
+def test_block_link_matches_separate_gate_backward(precision):
+    """ops.BlockLink: block i's MLP gate backward fused into block i+1's LayerNorm backward (sit.py:134-137 autograd) against
+    the separate launches - same kernel arithmetic, so predictions and every gradient agree to atomics-ordering noise; the
+    projector tap after block 2 keeps that block unlinked (its output has two consumers)."""
+    from reed_b200 import ops
+    spec = ArchSpec(input_size=16, hidden_size=128, decoder_hidden_size=128, depth=5, num_heads=2, encoder_depth=2,
+                    z_dims=[64], z_types=["i"], projector_dim=128, num_classes=10)
+    sd = random_state(spec, 5)
+    data = random_batch(spec, 6, 6)
+    x, y = data["x"].to(DEV), data["y"].to(DEV)
+    t = torch.linspace(0.1, 0.9, 6, device=DEV)
+    results = []
+    for linked in (True, False):
+        old = ops._BLOCK_LINK
+        ops._BLOCK_LINK = linked
+        try:
+            model = _build(spec, sd, precision).eval()
+            launches = ops.launch_count
+            pred, zs = model(x, t, y, inference=False)
+            ((pred.float() ** 2).mean() + (zs[0].float() ** 2).mean()).backward()
+            results.append((pred.detach().float(), {n: p.grad.detach().float().clone() for n, p in model.named_parameters()
+                                                    if p.grad is not None}, ops.launch_count - launches))
+        finally:
+            ops._BLOCK_LINK = old
+    (p_l, g_l, n_l), (p_s, g_s, n_s) = results
+    assert n_s - n_l == 3                                # blocks 1, 3, 4 hand their gate backward to their successor
+    assert torch.equal(p_l, p_s)
+    for name in g_s:
+        assert _rel(g_l[name], g_s[name]) < (1e-5 if precision == "fp32" else 2e-3), name
