@@ -71,8 +71,9 @@ def main():
     # fp32 buffers: Adam's normalised step is at most lr = 1e-4 per step, and where the true gradient is zero (the key third
     # of attn.qkv.bias - softmax is invariant to it) the sign of the computed gradient is rounding noise: two arithmetic
     # paths (atomics ordering; the NCCL-sharded trainer runs the adaLN linears per block, the replicated one grouped) can
-    # drift apart by lr per step.  Bound: 1.1 lr per step taken; bf16 shadows: one bf16 ulp of the value on top of that
-    drift = 1.1e-4 * (args.steps + 2)
+    # drift apart by up to 2 lr per step (+lr in one, -lr in the other; observed: 1.1 lr per step on a key bias).  Bound:
+    # 2.2 lr per step taken; bf16 shadows: one bf16 ulp of the value on top of that
+    drift = 2.2e-4 * (args.steps + 2)
     def excess(k):
         tol = drift + (n0[k].abs() * 2.0 ** -7 if k.endswith("/shadow") else 0.0)
         return float(((n0[k] - n1[k]).abs() - tol).max())
