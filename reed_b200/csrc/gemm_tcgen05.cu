@@ -251,7 +251,9 @@ int gemm_tcgen05_grouped(int mode, const void* const* A, int64_t lda, const void
     REED_REQUIRE(K == groups * per_group && per_group % 64 == 0, "gemm_grouped: K = groups x k_per_group, k_per_group %% 64 == 0");
     REED_REQUIRE(N % 8 == 0, "gemm_grouped: N %% 8 == 0");
     gm.per_group = per_group / 64;          // in k-blocks
-    p = plan_gemm(M, N, K, 1, ep.bias == nullptr, 1, 256);
+    // split over the reduction (fp32 atomics, order-dependent last bits) only where it pays: short reductions run as plain
+    // data-parallel tiles and stay bit-reproducible run to run
+    p = plan_gemm(M, N, K, 1, ep.bias == nullptr && K >= 16384, 1, 256);
     if (p.stream_k > 1 && !ep.accumulate) REED_CHECK_CUDA(cudaMemset2DAsync(D, (size_t)ldd * 4, 0, (size_t)N * 4, (size_t)M, st));
     for (int g = 0; g < groups; ++g) {
       REED_REQUIRE((((uintptr_t)A[g] | (uintptr_t)B[g]) & 15) == 0, "gemm_grouped: operand %d is not 16-byte aligned", g);

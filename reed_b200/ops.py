@@ -619,12 +619,13 @@ class BlockLink:
     LN-backward -> gate-backward kernel (the same one a block uses internally for its attention branch): block i+1 runs it with
     block i's saved branch output and gate, leaves dy / the bias-gradient handle / the modulation-gradient buffer here, and
     block i picks them up instead of launching its own gate backward (one launch and one 38 MB re-read of the residual
-    gradient less per block).  REED_BLOCK_LINK=0 turns it off for A/B runs."""
-    __slots__ = ("y", "gate", "bias", "ada", "dy", "db_ret", "dmod", "dx_ptr")
+    gradient less per block).  Should block i receive a different gradient after all (its output had another consumer, e.g.
+    a user hook that taps the residual stream), the gate backward of the difference is added - the operation is linear in
+    the incoming gradient.  REED_BLOCK_LINK=0 turns it off for A/B runs."""
+    __slots__ = ("y", "gate", "bias", "ada", "dy", "db_buf", "db_ret", "dmod", "dx")
 
     def __init__(self):
-        self.y = self.gate = self.bias = self.ada = self.dy = self.db_ret = self.dmod = None
-        self.dx_ptr = 0
+        self.y = self.gate = self.bias = self.ada = self.dy = self.db_buf = self.db_ret = self.dmod = self.dx = None
 
 
 _BLOCK_LINK = _os.environ.get("REED_BLOCK_LINK", "1") != "0"
@@ -707,9 +708,6 @@ class SiTBlockFn(torch.autograd.Function):
         handed = ctx.link_out if (ctx.link_out is not None and ctx.link_out.dy is not None) else None
         if handed is not None:
             # the next block's backward already ran this block's MLP gate backward on the gradient it produced
-            if dx2.data_ptr() != handed.dx_ptr:
-                raise RuntimeError("reed_b200: a linked block received a gradient other than the one its successor produced "
-                                   "(its output has another consumer); build the model without BlockLink for this block")
             dmod = handed.dmod
         else:
             dmod = ctx.ada[0].dmod(ctx.ada[1]) if ctx.ada is not None else torch.zeros_like(mod)
@@ -727,7 +725,10 @@ class SiTBlockFn(torch.autograd.Function):
         # ---- MLP branch:  x2 = x1 + g_m * (gelu(xm2 W1^T + b1) W2^T + b2)
         if handed is not None:
             dy2, db2 = handed.dy, handed.db_ret
-            handed.dy = handed.db_ret = handed.dmod = None
+            if dx2.data_ptr() != handed.dx.data_ptr():
+                # another consumer contributed to this block's output gradient: gate backward of the rest (linear in dx)
+                dy2 = dy2 + gate_bwd((dx2 - handed.dx).contiguous(), y2, g_m, T, dg_m, handed.db_buf)
+            handed.dy = handed.db_buf = handed.db_ret = handed.dmod = handed.dx = None
         else:
             db2_buf, db2 = bias_buffer(b_fc2)
             dy2 = gate_bwd(dx2, y2, g_m, T, dg_m, db2_buf)
@@ -766,7 +767,7 @@ class SiTBlockFn(torch.autograd.Function):
             dbq_buf, dbq_ret = bias_buffer(L.bias)
             dx0, dy_prev = ln_modulate_gate_bwd(dxm1, x0, mean1, rstd1, sc_a, T, dx1, dsh_a, dsc_a, L.y, L.gate,
                                                 dmod_prev[:, 5 * D:6 * D], dbq_buf)
-            L.dy, L.db_ret, L.dmod, L.dx_ptr = dy_prev, dbq_ret, dmod_prev, dx0.data_ptr()
+            L.dy, L.db_buf, L.db_ret, L.dmod, L.dx = dy_prev, dbq_buf, dbq_ret, dmod_prev, dx0
         else:
             dx0 = ln_modulate_bwd(dxm1, x0, mean1, rstd1, sc_a, T, dx1, dsh_a, dsc_a)
 

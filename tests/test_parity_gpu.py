@@ -307,10 +307,15 @@ def test_trainer_graph_replay_matches_eager(precision):
         assert abs(a - b) <= tol * max(1.0, abs(a)), (l_e, l_g)
     # Adam normalises the update: where a gradient is ~0 an atomics-ordering difference in its last bits can move a
     # parameter by a fraction of lr = 1e-4 per step (bf16 mode accumulates bias/modulation gradients with fp32 atomics)
+    # (the adaLN weight gradient is an fp32 outer product of the atomically accumulated dmod: where it is ~0 two runs can
+    # step lr apart in opposite directions, so a few elements may differ by up to 2 lr per step; all but 0.1 % stay tight)
     ptol = 2e-5 if precision == "fp32" else 2.5e-4
+    pmax = ptol if precision == "fp32" else 2.2e-4 * 5
     for k in p_e:
-        assert float((p_e[k] - p_g[k]).abs().max()) <= ptol, k
-        assert float((ema_e[k] - ema_g[k]).abs().max()) <= ptol, k
+        for a, b in ((p_e[k], p_g[k]), (ema_e[k], ema_g[k])):
+            d = (a - b).abs()
+            assert float(d.max()) <= pmax, k
+            assert float((d > ptol).float().mean()) <= 1e-3, k
 
 
 def test_full_size_properties_xl2_bf16():
@@ -415,3 +420,33 @@ def test_block_link_matches_separate_gate_backward(precision):
     assert torch.equal(p_l, p_s)
     for name in g_s:
         assert _rel(g_l[name], g_s[name]) < (1e-5 if precision == "fp32" else 2e-3), name
+
+
+def test_block_link_with_an_extra_consumer_of_the_residual_stream():
+    """A user hook taps the output of a linked block (a second consumer of the residual stream): the linked block adds the
+    gate backward of the extra gradient, results equal the unlinked model's."""
+    from reed_b200 import ops
+    spec = ArchSpec(input_size=16, hidden_size=128, decoder_hidden_size=128, depth=4, num_heads=2, encoder_depth=1,
+                    z_dims=[64], z_types=["i"], projector_dim=128, num_classes=10)
+    sd = random_state(spec, 7)
+    data = random_batch(spec, 4, 8)
+    x, y = data["x"].to(DEV), data["y"].to(DEV)
+    t = torch.linspace(0.2, 0.8, 4, device=DEV)
+    results = []
+    for linked in (True, False):
+        old = ops._BLOCK_LINK
+        ops._BLOCK_LINK = linked
+        try:
+            model = _build(spec, sd, "bf16").eval()
+            tapped = []
+            hook = model.blocks[2].register_forward_hook(lambda _m, _i, out: tapped.append(out))
+            pred, _ = model(x, t, y, inference=False)
+            hook.remove()
+            ((pred.float() ** 2).mean() + 0.3 * (tapped[0] ** 2).mean()).backward()
+            results.append({n: p.grad.detach().float().clone() for n, p in model.named_parameters() if p.grad is not None})
+        finally:
+            ops._BLOCK_LINK = old
+    g_l, g_s = results
+    for name in g_s:
+        cos = F.cosine_similarity(g_l[name].flatten(), g_s[name].flatten(), dim=0)
+        assert float(cos) > 0.9999 and _rel(g_l[name], g_s[name]) < 2e-2, (name, float(cos))
