@@ -69,7 +69,7 @@ int reed_outer_wgrad(const void* dy, int dy_dtype, int64_t ld_dy, const void* x,
 
 /* Several Linear layers that share their input, as ONE tensor-core launch: the adaLN-Zero modulation linears of all
  * transformer blocks, `adaLN_modulation(c)` of models/sit.py:125-133 (28 x [6D, D] weights in separate allocations, the same
- * silu(c) input) and the gradient of that shared input.  bf16 operands, fp32 D, M <= 128 rows, groups <= 32.
+ * silu(c) input) and the gradient of that shared input.  bf16 operands, fp32 D, M <= 1024 rows, groups <= 32.
  * A / B are HOST arrays of `groups` device pointers (mode 0 reads A[0] only); enqueue-only and graph-capturable.
  *   mode 0: D[M, groups * per_group] = A[0][M,K] . [B_0; B_1; ...]^T + bias[groups * per_group]   (B_g [per_group, K], pitch ldb;
  *           per_group % 256 == 0) - block g's modulation vectors are columns g * per_group ... of D.

@@ -125,7 +125,7 @@ extern "C" int reed_outer_wgrad(const void* dy, int dy_dtype, int64_t ld_dy, con
 }
 
 // Several linears that share their input as ONE tensor-core launch (the adaLN-Zero modulation linears of all blocks,
-// sit.py:125-133; bf16 operands, fp32 D, M <= 128).  A / B: host arrays of `groups` device pointers.
+// sit.py:125-133; bf16 operands, fp32 D, M <= 1024).  A / B: host arrays of `groups` device pointers.
 //   mode 0: D[M, groups * per_group] = A[0] . [B_0; B_1; ...]^T + bias      (B_g: [per_group, K] row-major)
 //   mode 1: D[M, N] (+)= sum_g A_g[M, per_group] . B_g[per_group, N]        (the input gradient of mode 0)
 extern "C" int reed_gemm_grouped(int mode, const void* const* A, int64_t lda, const void* const* B, int64_t ldb, int groups,

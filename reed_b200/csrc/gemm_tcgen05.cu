@@ -225,13 +225,13 @@ int gemm_tcgen05(const void* A, int64_t lda, int a_mn, const void* B, int64_t ld
   return gemm_tc_launch_cg1(p.bn, a_mn, b_mn, ma, mb, D, ldd, d_dtype, M, N, K, ep, st, p.grid, p.stream_k, emp);
 }
 
-// Grouped operands (see GroupMaps in gemm_tcgen05.cuh).  A: [M, K] K-major bf16, M <= 128 (one row tile).
+// Grouped operands (see GroupMaps in gemm_tcgen05.cuh).  A: [M, K] K-major bf16, M <= 1024 (cta_group::1 row tiles).
 //   mode 0: D[M, groups * n_per_group] = A . [B_0; B_1; ...]^T + bias, B_g [n_per_group, K] K-major (separate allocations)
 //   mode 1: D[M, N] (+)= sum_g A_g[M, k_per_group] . B_g[k_per_group, N], B_g MN-major; split over k, fp32 atomics
 int gemm_tcgen05_grouped(int mode, const void* const* A, int64_t lda, const void* const* B, int64_t ldb, int groups, int per_group,
                          void* D, int64_t ldd, int M, int N, int K, const EpiParams& ep, cudaStream_t st) {
   REED_REQUIRE(groups >= 1 && groups <= kMaxGroups, "gemm_grouped: %d groups (1..%d)", groups, kMaxGroups);
-  REED_REQUIRE(M >= 1 && M <= 128, "gemm_grouped: M = %d (a single row tile, <= 128)", M);
+  REED_REQUIRE(M >= 1 && M <= 1024, "gemm_grouped: M = %d (the shared input of the grouped linears has at most 1024 rows)", M);
   REED_REQUIRE(lda % 8 == 0 && ldb % 8 == 0 && ldd % 4 == 0, "gemm_grouped: row pitches must keep 16-byte alignment");
   REED_REQUIRE(ep.kind == kEpiNone && ep.out2 == nullptr && ep.bias_grad == nullptr, "gemm_grouped: plain fp32 output only");
   GroupMaps gm;             // ~8 KB, copied into the launch

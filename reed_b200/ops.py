@@ -395,6 +395,9 @@ def _bias_grad(p, dy2d):
     return out
 
 
+OUTER_WGRAD_MAX_ROWS = 64      # reed_outer_wgrad stages the whole batch in shared memory
+
+
 def outer_wgrad(dy, x, dw, db, accumulate):
     """dw[N,K] (+)= dy^T x and db[N] += colsum(dy) for a handful of rows (the batch is the contraction): reed_outer_wgrad.
     dy [B,N] fp32 or bf16, x [B,K]; db may be None."""
@@ -479,6 +482,7 @@ class _GradAccumulator:
 
 
 ADALN_GROUP_MAX = 32       # kMaxGroups of reed_gemm_grouped
+ADALN_GROUP_MAX_ROWS = 1024
 
 
 class AdaLNAll:
@@ -506,7 +510,7 @@ class AdaLNAll:
     def usable(c_act, linears, act_dtype):
         w = linears[0].weight
         return (act_dtype == torch.bfloat16 and c_act.dtype == torch.bfloat16 and 1 <= len(linears) <= ADALN_GROUP_MAX
-                and c_act.shape[0] <= 128 and w.shape[0] % 256 == 0 and w.shape[1] % 8 == 0 and w.shape[1] >= 64
+                and c_act.shape[0] <= ADALN_GROUP_MAX_ROWS and w.shape[0] % 256 == 0 and w.shape[1] % 8 == 0 and w.shape[1] >= 64
                 and _ADALN_GROUPED and (_gemm_backend & 7) != BACKEND_SIMT
                 and all(l.weight.shape == w.shape and l.bias is not None for l in linears))
 
@@ -776,7 +780,12 @@ class SiTBlockFn(torch.autograd.Function):
         if ctx.ada is not None:
             # weight and bias gradient in one outer-product pass over the fp32 dmod; the block's share of dL/d silu(c) is
             # part of one grouped GEMM over all blocks, run when that gradient is collected (AdaLNAll._input_grad)
-            dw_ada, db_ada = off_stream(lambda: _outer_weight_and_bias_grad(w_ada, b_ada, dmod, c_act), dmod, c_act)
+            if dmod.shape[0] <= OUTER_WGRAD_MAX_ROWS:
+                dw_ada, db_ada = off_stream(lambda: _outer_weight_and_bias_grad(w_ada, b_ada, dmod, c_act), dmod, c_act)
+            else:                         # a larger batch: the contraction is long enough for the tensor-core weight gradient
+                dmod_a = cast(dmod, act_dtype)
+                db_ada = _bias_grad(b_ada, dmod)
+                dw_ada = off_stream(lambda: _weight_grad(w_ada, dmod_a, c_act), dmod_a, c_act)
             ctx.ada[0].done.append(ctx.ada[1])
             if side is not None:
                 side.join()

@@ -154,7 +154,7 @@ def test_gemm_tma_epilogue_many_tiles(ops, bn):
     assert _rel(got.float(), want) < 1.5e-2
 
 
-@pytest.mark.parametrize("shape", [(32, 1152, 28), (4, 128, 2), (128, 384, 5), (7, 768, 12)])      # (batch, width, blocks)
+@pytest.mark.parametrize("shape", [(32, 1152, 28), (4, 128, 2), (128, 384, 5), (7, 768, 12), (256, 768, 12), (200, 128, 3)])   # (batch, width, blocks)
 def test_gemm_grouped_adaln(ops, shape):
     """reed_gemm_grouped: adaLN_modulation(c) of all blocks (sit.py:125-133) as one launch over separately stored weights,
     and the gradient of the shared input as one split-K launch over the concatenated reduction."""

@@ -360,16 +360,17 @@ def test_full_size_properties_xl2_bf16():
     assert float((p1[perm] - p2).abs().max()) < 1e-5 * max(1.0, float(p1.abs().max()))
 
 
-def test_grouped_adaln_matches_per_block_gemms():
+@pytest.mark.parametrize("batch", [6, 96])           # 96 > 64 rows: the modulation weight gradient leaves the outer-product kernel
+def test_grouped_adaln_matches_per_block_gemms(batch):
     """adaLN_modulation(c) of all blocks as one grouped GEMM + one grouped input-gradient GEMM (ops.AdaLNAll) against the
     per-block GEMMs it replaces (sit.py:125-133): same predictions, same gradients for every parameter upstream of c."""
     from reed_b200 import ops
     spec = ArchSpec(input_size=16, hidden_size=128, decoder_hidden_size=128, depth=5, num_heads=2, encoder_depth=2,
                     z_dims=[64], z_types=["i"], projector_dim=128, num_classes=10)
     sd = random_state(spec, 3)
-    data = random_batch(spec, 6, 4)
+    data = random_batch(spec, batch, 4)
     x, y = data["x"].to(DEV), data["y"].to(DEV)
-    t = torch.linspace(0.1, 0.9, 6, device=DEV)
+    t = torch.linspace(0.1, 0.9, batch, device=DEV)
     results = []
     for grouped in (True, False):
         old = ops._ADALN_GROUPED
