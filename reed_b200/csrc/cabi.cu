@@ -44,7 +44,7 @@ bool attn_fa_bwd_supported(int T, int hd);
 
 using namespace reed;
 
-extern "C" int reed_version(void) { return 100; }   // 0.1.0
+extern "C" int reed_version(void) { return 102; }   // 0.1.2: row backward entries take ld_dmod; reed_gemm_grouped, reed_outer_wgrad
 
 extern "C" const char* reed_last_error(void) { return g_err; }
 
